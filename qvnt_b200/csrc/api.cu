@@ -1,0 +1,643 @@
+// api.cu -- the C ABI (include/qvnt_b200.h): register lifetime, measurement,
+// data movement, instrumentation.  The hot path (qvnt_reg_apply) is scheduled in
+// planner.cu.  Reference functions replaced are cited in the header.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "reg.h"
+
+namespace qv {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return e == cudaErrorMemoryAllocation ? QVNT_ERR_OOM : QVNT_ERR_CUDA;
+}
+
+int ensure_dev(void **p, size_t *cap, size_t bytes) {
+    if (*cap >= bytes && *p) return QVNT_OK;
+    if (*p) QV_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    size_t want = bytes < 4096 ? 4096 : bytes;
+    QV_CUDA(cudaMalloc(p, want));
+    *cap = want;
+    return QVNT_OK;
+}
+
+// Pinned staging buffer the op descriptors are copied from.  Before the host
+// overwrites it, wait until the previous H2D copy out of it has executed.
+int ensure_stage(qvnt_reg *r, size_t bytes) {
+    if (r->stage_busy) {
+        QV_CUDA(cudaEventSynchronize(r->stage_free));
+        r->stage_busy = false;
+    }
+    if (r->h_stage_cap >= bytes) return QVNT_OK;
+    if (r->h_stage) QV_CUDA(cudaFreeHost(r->h_stage));
+    r->h_stage = nullptr;
+    r->h_stage_cap = 0;
+    size_t want = bytes < (1u << 16) ? (1u << 16) : bytes;
+    QV_CUDA(cudaMallocHost(&r->h_stage, want));
+    r->h_stage_cap = want;
+    return QVNT_OK;
+}
+
+LaunchScope::LaunchScope(qvnt_reg *reg, int c) : r(reg), cls(c) {
+    if (!r->opt_profile) return;
+    auto get = [&]() {
+        cudaEvent_t e;
+        if (!r->event_pool.empty()) {
+            e = r->event_pool.back();
+            r->event_pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        return e;
+    };
+    a = get();
+    b = get();
+    cudaEventRecord(a, r->stream);
+}
+void LaunchScope::done(int n_launches) {
+    if (n_launches > 0) r->stats.launches[cls] += (uint64_t)n_launches;
+    if (!r->opt_profile) return;
+    cudaEventRecord(b, r->stream);
+    r->timed.push_back({cls, a, b});
+}
+
+static int fold_timed(qvnt_reg *r) {
+    if (r->timed.empty()) return QVNT_OK;
+    QV_CUDA(cudaStreamSynchronize(r->stream));
+    for (auto &t : r->timed) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t.a, t.b);
+        r->stats.ms[t.cls] += (double)ms;
+        r->event_pool.push_back(t.a);
+        r->event_pool.push_back(t.b);
+    }
+    r->timed.clear();
+    return QVNT_OK;
+}
+
+static int use(const qvnt_reg *r) {
+    if (!r) {
+        set_error("null register handle");
+        return QVNT_ERR_INVALID;
+    }
+    QV_CUDA(cudaSetDevice(r->device));
+    return QVNT_OK;
+}
+
+static uint64_t rank_bits(const qvnt_reg *r) { return (uint64_t)r->rank << r->n_local; }
+
+static int init_state(qvnt_reg *r, uint64_t state) {
+    state &= r->q_mask;
+    const uint64_t owner = state >> r->n_local;
+    const uint64_t local = state & (r->local_len - 1);
+    LaunchScope ls(r, 3);
+    int n = launch_set_basis(r->stream, r->psi, r->local_len, owner == r->rank ? local : ~0ull);
+    ls.done(n);
+    r->stats.alg_bytes[3] += r->local_len * 16;
+    if (n < 0) return cuda_fail(cudaGetLastError(), "set_basis");
+    return QVNT_OK;
+}
+
+static int create_common(uint32_t q_num, uint64_t state, uint32_t rank, uint32_t world, int device,
+                         qvnt_reg_t **out) {
+    if (!out) {
+        set_error("null out pointer");
+        return QVNT_ERR_INVALID;
+    }
+    *out = nullptr;
+    if (world == 0 || world > (uint32_t)MAX_WORLD || (world & (world - 1)) || rank >= world) {
+        set_error("world must be 1/2/4/8 and rank < world (got rank %u world %u)", rank, world);
+        return QVNT_ERR_INVALID;
+    }
+    uint32_t wb = 0;
+    while ((1u << wb) < world) ++wb;
+    if (q_num > 40 || q_num < wb) {
+        set_error("q_num %u out of range for world %u", q_num, world);
+        return QVNT_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("no CUDA device available (%s); this library has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return QVNT_ERR_CUDA;
+    }
+    if (device < 0) QV_CUDA(cudaGetDevice(&device));
+    if (device >= ndev) {
+        set_error("device %d out of range (%d devices)", device, ndev);
+        return QVNT_ERR_INVALID;
+    }
+    QV_CUDA(cudaSetDevice(device));
+    qvnt_reg *r = new (std::nothrow) qvnt_reg();
+    if (!r) return QVNT_ERR_OOM;
+    r->device = device;
+    cudaDeviceGetAttribute(&r->sm_count, cudaDevAttrMultiProcessorCount, device);
+    r->q_num = q_num;
+    r->rank = rank;
+    r->world = world;
+    r->world_bits = wb;
+    r->n_local = q_num - wb;
+    r->q_mask = q_num >= 64 ? ~0ull : ((1ull << q_num) - 1ull);
+    r->local_len = 1ull << r->n_local;
+    int rc = QVNT_OK;
+    auto fail = [&](int code) {
+        qvnt_reg_destroy(r);
+        return code;
+    };
+    if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(cuda_fail(cudaGetLastError(), "cudaStreamCreate"));
+    e = cudaMalloc((void **)&r->psi, r->local_len * sizeof(amp));
+    if (e != cudaSuccess) {
+        set_error("cannot allocate %llu bytes of HBM for a %u-qubit shard: %s",
+                  (unsigned long long)(r->local_len * sizeof(amp)), r->n_local, cudaGetErrorString(e));
+        cudaGetLastError();
+        return fail(QVNT_ERR_OOM);
+    }
+    if (cudaMalloc((void **)&r->d_partials, REDUCE_BLOCKS_MAX * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&r->d_scalars, 16 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc((void **)&r->d_result, 8 * sizeof(uint64_t)) != cudaSuccess ||
+        cudaMalloc((void **)&r->mailbox, 4096) != cudaSuccess ||
+        cudaMallocHost((void **)&r->h_scalars, 32 * sizeof(double)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r->stage_free, cudaEventDisableTiming) != cudaSuccess)
+        return fail(cuda_fail(cudaGetLastError(), "scratch allocation"));
+    QV_CUDA(cudaMemsetAsync(r->mailbox, 0, 4096, r->stream));
+    for (int i = 0; i < MAX_WORLD; ++i) r->segs.seg[i] = nullptr;
+    r->segs.seg[rank] = r->psi;
+    r->segs.shift = r->n_local;
+    r->segs.rank = rank;
+    r->segs.world_bits = wb;
+    r->mail[rank] = r->mailbox;
+    rc = init_state(r, state);
+    if (rc != QVNT_OK) return fail(rc);
+    *out = r;
+    return QVNT_OK;
+}
+
+static int norm_sqr_local(qvnt_reg *r, double *out) {
+    LaunchScope ls(r, 2);
+    int n = launch_norm_sqr(r->stream, r->psi, r->local_len, r->d_partials, r->d_scalars, r->sm_count);
+    ls.done(n);
+    r->stats.alg_bytes[2] += r->local_len * 16;
+    if (n < 0) return cuda_fail(cudaGetLastError(), "norm_sqr");
+    QV_CUDA(cudaMemcpyAsync(r->h_scalars, r->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, r->stream));
+    QV_CUDA(cudaStreamSynchronize(r->stream));
+    r->stats.d2h_bytes += sizeof(double);
+    *out = r->h_scalars[0];
+    return QVNT_OK;
+}
+
+// sum |a|^2 over the whole register (all shards, accumulated in rank order)
+static int norm_sqr_global(qvnt_reg *r, double *out) {
+    double local = 0.0;
+    int rc = norm_sqr_local(r, &local);
+    if (rc) return rc;
+    if (r->world == 1) {
+        *out = local;
+        return QVNT_OK;
+    }
+    double all[MAX_WORLD];
+    rc = dist_allgather_double(r, local, all);
+    if (rc) return rc;
+    double s = 0.0;
+    for (uint32_t k = 0; k < r->world; ++k) s += all[k];
+    *out = s;
+    return QVNT_OK;
+}
+
+static int normalize_impl(qvnt_reg *r) {
+    double n2 = 0.0;
+    int rc = norm_sqr_global(r, &n2);
+    if (rc) return rc;
+    const double norm = sqrt(n2);
+    if (norm <= 1e-15) return init_state(r, 0);      // quant.rs:399-402
+    if (1.0 - norm <= 1e-9) return QVNT_OK;          // quant.rs:403-405
+    LaunchScope ls(r, 3);
+    int n = launch_scale(r->stream, r->psi, r->local_len, 1.0 / norm);
+    ls.done(n);
+    r->stats.alg_bytes[3] += r->local_len * 32;
+    return n < 0 ? cuda_fail(cudaGetLastError(), "scale") : QVNT_OK;
+}
+
+static int collapse_impl(qvnt_reg *r, uint64_t idy, uint64_t mask) {
+    LaunchScope ls(r, 3);
+    int n = launch_collapse(r->stream, r->psi, r->local_len, rank_bits(r), idy, mask);
+    ls.done(n);
+    r->stats.alg_bytes[3] += r->local_len * 16;   // write-only: zeroes the mismatching amplitudes
+    return n < 0 ? cuda_fail(cudaGetLastError(), "collapse") : QVNT_OK;
+}
+
+static int check_local_range(qvnt_reg *r, uint64_t off, uint64_t cnt, uint64_t *local_off) {
+    const uint64_t lo = rank_bits(r);
+    if (off < lo || cnt > r->local_len || off - lo > r->local_len - cnt) {
+        set_error("range [%llu, +%llu) is outside rank %u's shard", (unsigned long long)off,
+                  (unsigned long long)cnt, r->rank);
+        return QVNT_ERR_INVALID;
+    }
+    *local_off = off - lo;
+    return QVNT_OK;
+}
+
+}  // namespace qv
+
+using namespace qv;
+
+extern "C" {
+
+int qvnt_version(void) { return QVNT_B200_VERSION; }
+const char *qvnt_last_error(void) { return qv::g_err; }
+
+int qvnt_device_count(int *out) {
+    if (!out) return QVNT_ERR_INVALID;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *out = n;
+    return QVNT_OK;
+}
+
+int qvnt_reg_create(uint32_t q_num, uint64_t state, qvnt_reg_t **out) {
+    return create_common(q_num, state, 0, 1, -1, out);
+}
+
+int qvnt_reg_create_sharded(uint32_t q_num, uint64_t state, uint32_t rank, uint32_t world, int device,
+                            qvnt_reg_t **out) {
+    return create_common(q_num, state, rank, world, device, out);
+}
+
+int qvnt_reg_destroy(qvnt_reg_t *r) {
+    if (!r) return QVNT_OK;
+    cudaSetDevice(r->device);
+    if (r->stream) cudaStreamSynchronize(r->stream);
+    for (int i = 0; i < MAX_WORLD; ++i) {
+        if (r->peer_ptr[i]) cudaIpcCloseMemHandle(r->peer_ptr[i]);
+        if (r->peer_mail[i]) cudaIpcCloseMemHandle(r->peer_mail[i]);
+    }
+    for (auto &t : r->timed) {
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    for (auto e : r->event_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 16; ++i)
+        if (r->marks[i]) cudaEventDestroy(r->marks[i]);
+    if (r->stage_free) cudaEventDestroy(r->stage_free);
+    cudaFree(r->psi);
+    cudaFree(r->d_partials);
+    cudaFree(r->d_scalars);
+    cudaFree(r->d_result);
+    cudaFree(r->d_l1);
+    cudaFree(r->d_l2);
+    cudaFree(r->d_tmp);
+    cudaFree(r->d_ops);
+    cudaFree(r->d_mat);
+    cudaFree(r->mailbox);
+    if (r->h_stage) cudaFreeHost(r->h_stage);
+    if (r->h_scalars) cudaFreeHost(r->h_scalars);
+    if (r->stream) cudaStreamDestroy(r->stream);
+    cudaGetLastError();
+    delete r;
+    return QVNT_OK;
+}
+
+int qvnt_reg_clone(qvnt_reg_t *r, qvnt_reg_t **out) {
+    int rc = use(r);
+    if (rc) return rc;
+    if (r->world != 1) {
+        set_error("clone of a sharded register: create a new sharded register and copy shards");
+        return QVNT_ERR_UNSUPPORTED;
+    }
+    rc = create_common(r->q_num, 0, 0, 1, r->device, out);
+    if (rc) return rc;
+    qvnt_reg *c = *out;
+    QV_CUDA(cudaStreamSynchronize(c->stream));
+    QV_CUDA(cudaMemcpyAsync(c->psi, r->psi, r->local_len * sizeof(amp), cudaMemcpyDeviceToDevice, r->stream));
+    QV_CUDA(cudaStreamSynchronize(r->stream));
+    c->opt_fuse = r->opt_fuse;
+    c->opt_tile_bits = r->opt_tile_bits;
+    c->opt_chunk_bits = r->opt_chunk_bits;
+    c->opt_tma = r->opt_tma;
+    return QVNT_OK;
+}
+
+int qvnt_reg_q_num(const qvnt_reg_t *r, uint32_t *out) {
+    if (!r || !out) return QVNT_ERR_INVALID;
+    *out = r->q_num;
+    return QVNT_OK;
+}
+
+int qvnt_reg_apply(qvnt_reg_t *r, const qvnt_op_t *ops, size_t n_ops) {
+    int rc = use(r);
+    if (rc) return rc;
+    if (n_ops == 0) return QVNT_OK;
+    if (!ops) {
+        set_error("null op array");
+        return QVNT_ERR_INVALID;
+    }
+    return run_ops(r, ops, n_ops);
+}
+
+int qvnt_reg_norm_sqr(qvnt_reg_t *r, double *out) {
+    int rc = use(r);
+    if (rc) return rc;
+    if (!out) return QVNT_ERR_INVALID;
+    return norm_sqr_global(r, out);
+}
+
+static int stream_out(qvnt_reg *r, uint64_t loff, uint64_t cnt, double *host, int per, double inv) {
+    // per = doubles per amplitude in the output (1: probabilities, 2: polar)
+    const uint64_t chunk = 1ull << 21;
+    int rc = ensure_dev((void **)&r->d_tmp, &r->tmp_cap,
+                        (size_t)(cnt < chunk ? cnt : chunk) * per * sizeof(double));
+    if (rc) return rc;
+    for (uint64_t done = 0; done < cnt; done += chunk) {
+        const uint64_t c = cnt - done < chunk ? cnt - done : chunk;
+        LaunchScope ls(r, 2);
+        int n = per == 1 ? launch_probabilities(r->stream, r->psi, loff + done, c, inv, r->d_tmp)
+                         : launch_polar(r->stream, r->psi, loff + done, c, r->d_tmp);
+        ls.done(n);
+        if (n < 0) return cuda_fail(cudaGetLastError(), "probabilities");
+        QV_CUDA(cudaMemcpyAsync(host + done * per, r->d_tmp, c * per * sizeof(double), cudaMemcpyDeviceToHost,
+                                r->stream));
+        QV_CUDA(cudaStreamSynchronize(r->stream));
+        r->stats.d2h_bytes += c * per * sizeof(double);
+    }
+    return QVNT_OK;
+}
+
+int qvnt_reg_probabilities(qvnt_reg_t *r, uint64_t off, uint64_t cnt, double *host_out) {
+    int rc = use(r);
+    if (rc) return rc;
+    if (cnt == 0) return QVNT_OK;
+    if (!host_out) return QVNT_ERR_INVALID;
+    uint64_t loff = 0;
+    if ((rc = check_local_range(r, off, cnt, &loff))) return rc;
+    double n2 = 0.0;
+    if ((rc = norm_sqr_global(r, &n2))) return rc;
+    return stream_out(r, loff, cnt, host_out, 1, 1.0 / n2);
+}
+
+int qvnt_reg_polar(qvnt_reg_t *r, uint64_t off, uint64_t cnt, double *host_r_theta) {
+    int rc = use(r);
+    if (rc) return rc;
+    if (cnt == 0) return QVNT_OK;
+    if (!host_r_theta) return QVNT_ERR_INVALID;
+    uint64_t loff = 0;
+    if ((rc = check_local_range(r, off, cnt, &loff))) return rc;
+    return stream_out(r, loff, cnt, host_r_theta, 2, 0.0);
+}
+
+int qvnt_reg_collapse(qvnt_reg_t *r, uint64_t idy, uint64_t mask) {
+    int rc = use(r);
+    if (rc) return rc;
+    return collapse_impl(r, idy, mask);
+}
+
+int qvnt_reg_measure_mask(qvnt_reg_t *r, uint64_t mask, double u01, uint64_t *outcome, uint64_t *sampled) {
+    int rc = use(r);
+    if (rc) return rc;
+    if (!outcome) return QVNT_ERR_INVALID;
+    if (!(u01 >= 0.0 && u01 < 1.0)) {
+        set_error("u01 must be in [0, 1)");
+        return QVNT_ERR_INVALID;
+    }
+    mask &= r->q_mask;
+    if (mask == 0) {                      // quant.rs:491-494
+        *outcome = 0;
+        if (sampled) *sampled = 0;
+        return QVNT_OK;
+    }
+    double n2 = 0.0;
+    if ((rc = norm_sqr_global(r, &n2))) return rc;
+    const double inv = 1.0 / n2;          // get_probabilities: abs = 1 / sum
+    const uint64_t n1 = (r->local_len + SAMPLE_BLOCK - 1) / SAMPLE_BLOCK;
+    const uint64_t n2b = (n1 + SAMPLE_BLOCK - 1) / SAMPLE_BLOCK;
+    if ((rc = ensure_dev((void **)&r->d_l1, &r->l1_cap, n1 * sizeof(double)))) return rc;
+    if ((rc = ensure_dev((void **)&r->d_l2, &r->l2_cap, n2b * sizeof(double)))) return rc;
+    {
+        LaunchScope ls(r, 2);
+        int n = launch_block_weights(r->stream, r->psi, r->local_len, inv, r->d_l1, r->d_l2);
+        int m = launch_total(r->stream, r->d_l2, n2b, r->d_scalars + 1);
+        ls.done(n + m);
+        r->stats.alg_bytes[2] += r->local_len * 16;
+        if (n < 0 || m < 0) return cuda_fail(cudaGetLastError(), "block_weights");
+    }
+    QV_CUDA(cudaMemcpyAsync(r->h_scalars, r->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, r->stream));
+    QV_CUDA(cudaStreamSynchronize(r->stream));
+    r->stats.d2h_bytes += sizeof(double);
+    const double my_total = r->h_scalars[0];
+    double totals[MAX_WORLD] = {my_total};
+    if (r->world > 1 && (rc = dist_allgather_double(r, my_total, totals))) return rc;
+    double total = 0.0, prefix = 0.0;
+    for (uint32_t k = 0; k < r->world; ++k) {
+        if (k == r->rank) prefix = total;
+        total += totals[k];
+    }
+    const double x = u01 * total;         // UniformFloat::sample: u * scale + low, low = 0
+    {
+        LaunchScope ls(r, 2);
+        int n = launch_locate(r->stream, r->psi, r->local_len, inv, r->d_l1, n1, r->d_l2, n2b, prefix, x,
+                              r->d_result);
+        ls.done(n);
+        if (n < 0) return cuda_fail(cudaGetLastError(), "locate");
+    }
+    uint64_t *hres = (uint64_t *)(r->h_scalars + 8);
+    QV_CUDA(cudaMemcpyAsync(hres, r->d_result, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost, r->stream));
+    QV_CUDA(cudaStreamSynchronize(r->stream));
+    r->stats.d2h_bytes += 3 * sizeof(uint64_t);
+    uint64_t idx;
+    if (r->world == 1) {
+        idx = hres[0];                     // not found => len-1 == partition_point's upper bound
+    } else {
+        // first rank (in rank order) whose shard contains the crossing; none => last index
+        uint64_t mine = hres[1] ? (rank_bits(r) | hres[0]) : ~0ull;
+        uint64_t all[MAX_WORLD];
+        if ((rc = dist_allgather_u64(r, mine, all))) return rc;
+        idx = r->q_mask;
+        for (uint32_t k = 0; k < r->world; ++k)
+            if (all[k] != ~0ull) {
+                idx = all[k];
+                break;
+            }
+    }
+    if ((rc = collapse_impl(r, idx, mask))) return rc;
+    *outcome = idx & mask;
+    if (sampled) *sampled = idx;
+    return QVNT_OK;
+}
+
+int qvnt_reg_measure_mask_rng(qvnt_reg_t *r, uint64_t mask, uint64_t *outcome) {
+    if (!r) return QVNT_ERR_INVALID;
+    // splitmix64 -> 53-bit uniform in [0,1); all ranks of a sharded register share the seed
+    uint64_t z = (r->rng_state += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    const double u = (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    return qvnt_reg_measure_mask(r, mask, u, outcome, nullptr);
+}
+
+int qvnt_reg_normalize(qvnt_reg_t *r) {
+    int rc = use(r);
+    if (rc) return rc;
+    return normalize_impl(r);
+}
+
+int qvnt_reg_reset(qvnt_reg_t *r, uint64_t state) {
+    int rc = use(r);
+    if (rc) return rc;
+    return init_state(r, state);
+}
+
+int qvnt_reg_reset_by_mask(qvnt_reg_t *r, uint64_t mask) {
+    int rc = use(r);
+    if (rc) return rc;
+    if ((mask & r->q_mask) == r->q_mask) return init_state(r, 0);   // quant.rs:208-210
+    {
+        LaunchScope ls(r, 3);
+        int n = launch_zero_mask(r->stream, r->psi, r->local_len, rank_bits(r), mask);
+        ls.done(n);
+        if (n < 0) return cuda_fail(cudaGetLastError(), "zero_mask");
+    }
+    return normalize_impl(r);
+}
+
+int qvnt_reg_read(qvnt_reg_t *r, uint64_t off, uint64_t cnt, double *host) {
+    int rc = use(r);
+    if (rc) return rc;
+    if (cnt == 0) return QVNT_OK;
+    if (!host) return QVNT_ERR_INVALID;
+    uint64_t loff = 0;
+    if ((rc = check_local_range(r, off, cnt, &loff))) return rc;
+    QV_CUDA(cudaMemcpyAsync(host, r->psi + loff, cnt * sizeof(amp), cudaMemcpyDeviceToHost, r->stream));
+    QV_CUDA(cudaStreamSynchronize(r->stream));
+    r->stats.d2h_bytes += cnt * sizeof(amp);
+    return QVNT_OK;
+}
+
+int qvnt_reg_write(qvnt_reg_t *r, uint64_t off, uint64_t cnt, const double *host) {
+    int rc = use(r);
+    if (rc) return rc;
+    if (cnt == 0) return QVNT_OK;
+    if (!host) return QVNT_ERR_INVALID;
+    uint64_t loff = 0;
+    if ((rc = check_local_range(r, off, cnt, &loff))) return rc;
+    QV_CUDA(cudaMemcpyAsync(r->psi + loff, host, cnt * sizeof(amp), cudaMemcpyHostToDevice, r->stream));
+    QV_CUDA(cudaStreamSynchronize(r->stream));
+    r->stats.h2d_bytes += cnt * sizeof(amp);
+    return QVNT_OK;
+}
+
+int qvnt_reg_tensor_prod(qvnt_reg_t *a, qvnt_reg_t *b, qvnt_reg_t **out) {
+    int rc = use(a);
+    if (rc) return rc;
+    if (!b || !out) return QVNT_ERR_INVALID;
+    if (a->world != 1 || b->world != 1 || a->device != b->device) {
+        set_error("tensor_prod needs two single-GPU registers on the same device");
+        return QVNT_ERR_UNSUPPORTED;
+    }
+    rc = create_common(a->q_num + b->q_num, 0, 0, 1, a->device, out);
+    if (rc) return rc;
+    qvnt_reg *o = *out;
+    QV_CUDA(cudaStreamSynchronize(a->stream));
+    QV_CUDA(cudaStreamSynchronize(b->stream));
+    LaunchScope ls(o, 3);
+    int n = launch_tensor_prod(o->stream, a->psi, a->q_num, b->psi, b->q_num, o->psi, 0, o->local_len);
+    ls.done(n);
+    if (n < 0) return cuda_fail(cudaGetLastError(), "tensor_prod");
+    QV_CUDA(cudaStreamSynchronize(o->stream));
+    return QVNT_OK;
+}
+
+int qvnt_reg_sync(qvnt_reg_t *r) {
+    int rc = use(r);
+    if (rc) return rc;
+    QV_CUDA(cudaStreamSynchronize(r->stream));
+    return QVNT_OK;
+}
+
+int qvnt_reg_set_option(qvnt_reg_t *r, const char *key, int64_t value) {
+    if (!r || !key) return QVNT_ERR_INVALID;
+    if (!strcmp(key, "fuse")) r->opt_fuse = value != 0;
+    else if (!strcmp(key, "tile_bits")) {
+        if (value != 0 && (value < 8 || value > TILE_MAX_BITS)) {
+            set_error("tile_bits must be 0 (auto) or 8..%d", TILE_MAX_BITS);
+            return QVNT_ERR_INVALID;
+        }
+        r->opt_tile_bits = (int)value;
+    } else if (!strcmp(key, "chunk_bits")) {
+        if (value != 0 && (value < 2 || value > TILE_MAX_BITS)) {
+            set_error("chunk_bits must be 0 (auto) or 2..%d", TILE_MAX_BITS);
+            return QVNT_ERR_INVALID;
+        }
+        r->opt_chunk_bits = (int)value;
+    } else if (!strcmp(key, "tma")) r->opt_tma = value != 0;
+    else if (!strcmp(key, "profile")) {
+        int rc = use(r);
+        if (rc) return rc;
+        if (!value) fold_timed(r);
+        r->opt_profile = value != 0;
+    } else if (!strcmp(key, "seed")) r->rng_state = (uint64_t)value;
+    else {
+        set_error("unknown option '%s'", key);
+        return QVNT_ERR_INVALID;
+    }
+    return QVNT_OK;
+}
+
+int qvnt_reg_stats(qvnt_reg_t *r, qvnt_stats_t *out) {
+    int rc = use(r);
+    if (rc) return rc;
+    if (!out) return QVNT_ERR_INVALID;
+    if ((rc = fold_timed(r))) return rc;
+    *out = r->stats;
+    return QVNT_OK;
+}
+
+int qvnt_reg_stats_reset(qvnt_reg_t *r) {
+    int rc = use(r);
+    if (rc) return rc;
+    if ((rc = fold_timed(r))) return rc;
+    memset(&r->stats, 0, sizeof(r->stats));
+    return QVNT_OK;
+}
+
+int qvnt_reg_mark(qvnt_reg_t *r, int slot) {
+    int rc = use(r);
+    if (rc) return rc;
+    if (slot < 0 || slot >= 16) return QVNT_ERR_INVALID;
+    if (!r->marks[slot]) QV_CUDA(cudaEventCreate(&r->marks[slot]));
+    QV_CUDA(cudaEventRecord(r->marks[slot], r->stream));
+    r->mark_set[slot] = true;
+    return QVNT_OK;
+}
+
+int qvnt_reg_elapsed_ms(qvnt_reg_t *r, int from, int to, double *ms) {
+    int rc = use(r);
+    if (rc) return rc;
+    if (from < 0 || from >= 16 || to < 0 || to >= 16 || !ms || !r->mark_set[from] || !r->mark_set[to])
+        return QVNT_ERR_INVALID;
+    QV_CUDA(cudaEventSynchronize(r->marks[to]));
+    float f = 0.f;
+    QV_CUDA(cudaEventElapsedTime(&f, r->marks[from], r->marks[to]));
+    *ms = (double)f;
+    return QVNT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+// reg.h -- the device-resident register behind the opaque qvnt_reg_t handle.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+struct qvnt_reg {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+
+    uint32_t q_num = 0;       // qubits of the whole register
+    uint32_t rank = 0, world = 1, world_bits = 0;
+    uint32_t n_local = 0;     // index bits held by this GPU
+    uint64_t q_mask = 0;      // 2^q_num - 1
+    uint64_t local_len = 1;   // 2^n_local amplitudes
+    qv::amp *psi = nullptr;   // this GPU's shard
+    qv::Segs segs{};          // all shards (peers mapped over NVLink IPC)
+    bool peers_attached = false;
+    void *peer_ptr[qv::MAX_WORLD] = {};     // opened IPC mappings (state)
+    void *peer_mail[qv::MAX_WORLD] = {};    // opened IPC mappings (mailbox)
+    // mailbox: cross-GPU barrier counters + small all-gather slots, IPC-shared
+    unsigned long long *mailbox = nullptr;  // this rank's mailbox (device memory)
+    unsigned long long *mail[qv::MAX_WORLD] = {};
+    uint64_t barrier_epoch = 0;
+    uint64_t gather_epoch = 0;
+
+    // scratch (device)
+    double *d_partials = nullptr;   // REDUCE_BLOCKS_MAX
+    double *d_scalars = nullptr;    // 16 doubles
+    uint64_t *d_result = nullptr;   // 8 words
+    double *d_l1 = nullptr, *d_l2 = nullptr;
+    size_t l1_cap = 0, l2_cap = 0;   // bytes
+    double *d_tmp = nullptr;        // probabilities / polar staging
+    size_t tmp_cap = 0;             // bytes
+    // op upload (device) + pinned staging (host)
+    void *d_ops = nullptr;
+    size_t d_ops_cap = 0;
+    qv::amp *d_mat = nullptr;
+    size_t d_mat_cap = 0;           // bytes
+    void *h_stage = nullptr;
+    size_t h_stage_cap = 0;
+    cudaEvent_t stage_free = nullptr;  // recorded after the last H2D copy out of h_stage
+    bool stage_busy = false;
+    double *h_scalars = nullptr;    // pinned, 32 doubles / words
+
+    // options
+    int opt_fuse = 1;
+    int opt_tile_bits = 0;          // 0 = auto
+    int opt_chunk_bits = 0;         // 0 = auto
+    int opt_tma = 1;
+    int opt_profile = 0;
+    uint64_t rng_state = 0x51564E54ull;
+
+    // instrumentation
+    qvnt_stats_t stats{};
+    struct Timed { int cls; cudaEvent_t a, b; };
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t marks[16] = {};
+    bool mark_set[16] = {};
+};
+
+namespace qv {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define QV_CUDA(expr)                                                      \
+    do {                                                                   \
+        cudaError_t _e = (expr);                                           \
+        if (_e != cudaSuccess) return qv::cuda_fail(_e, #expr);            \
+    } while (0)
+
+// profiling bracket around kernel launches of one class
+struct LaunchScope {
+    qvnt_reg *r;
+    int cls;
+    cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(qvnt_reg *reg, int c);
+    void done(int n_launches);
+};
+
+// planner.cu: validate + schedule + enqueue one op list
+int run_ops(qvnt_reg *r, const qvnt_op_t *ops, size_t n_ops);
+// multi-GPU plumbing (dist.cu)
+int dist_barrier(qvnt_reg *r);
+int dist_allgather_double(qvnt_reg *r, double v, double *out /* world */);
+int dist_allgather_u64(qvnt_reg *r, uint64_t v, uint64_t *out /* world */);
+int ensure_stage(qvnt_reg *r, size_t bytes);
+int ensure_dev(void **p, size_t *cap, size_t bytes);
+
+}  // namespace qv
