@@ -324,6 +324,6 @@ class QReg:
         """Rust `{:?}` of the register (quant.rs:603-623)."""
         n = min(1 << self.q_num, MAX_LEN_TO_DISPLAY)
         a = self.amplitudes(0, n)
-        body = ", ".join(f"{i}: {_rust_complex_debug(z.real, z.imag)}" for i, z in enumerate(a))
+        body = ", ".join(f"{i}: {_rust_complex_debug(float(z.real), float(z.imag))}" for i, z in enumerate(a))
         tail = "" if (1 << self.q_num) <= MAX_LEN_TO_DISPLAY else ", .."
         return f"QReg {{ {body}{tail} }}"
