@@ -214,6 +214,12 @@ def run_ours(args):
         reg.attach_peers(blobs)
     else:
         reg = QReg.new(n)
+    if args.tile_bits:
+        reg.set_option("tile_bits", args.tile_bits)
+    if args.chunk_bits:
+        reg.set_option("chunk_bits", args.chunk_bits)
+    if args.no_fuse:
+        reg.set_option("fuse", 0)
 
     def barrier():
         if dist is not None:
@@ -304,7 +310,8 @@ def run_ours(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": name, "qubits": n, "single_ops": n_ops, "state_bytes": 16 << n,
                    "l2": "state (>= 4 GiB) is far larger than the 126 MB L2; no flush needed",
-                   "sharding": f"top {world.bit_length() - 1} qubits across {world} GPU(s)"},
+                   "sharding": f"top {world.bit_length() - 1} qubits across {world} GPU(s)",
+                   "fuse": not args.no_fuse, "tile_bits": args.tile_bits or 12, "chunk_bits": args.chunk_bits or 7},
         "amplitude_gbs": value * 32 * (1 << n) / 1e9,
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
     }
@@ -331,6 +338,9 @@ def main():
     ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--tile-bits", type=int, default=0)
+    ap.add_argument("--chunk-bits", type=int, default=0)
+    ap.add_argument("--no-fuse", action="store_true", help="one in-place sweep per SingleOp")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -121,6 +121,13 @@ int qvnt_reg_q_num(const qvnt_reg_t *reg, uint32_t *out);          /* QReg::num 
  * sweep per SingleOp (dispatch.rs:32-67). */
 int qvnt_reg_apply(qvnt_reg_t *reg, const qvnt_op_t *ops, size_t n_ops);
 
+/* The schedule qvnt_reg_apply would run for this op list on rank `rank` of a q_num-qubit
+ * register sharded over `world` GPUs, as text (one line per pass / stage / op).  Host-only:
+ * needs no CUDA device.  tile_bits / chunk_bits 0 = defaults.  *needed = bytes incl. NUL. */
+int qvnt_plan_describe(uint32_t q_num, uint32_t rank, uint32_t world, int peers_attached, int fuse,
+                       int tile_bits, int chunk_bits, const qvnt_op_t *ops, size_t n_ops, char *out,
+                       size_t cap, size_t *needed);
+
 /* ---- measurement / normalisation ------------------------------------------ */
 int qvnt_reg_norm_sqr(qvnt_reg_t *reg, double *out);               /* get_absolute  quant.rs:458-466 */
 /* get_probabilities (quant.rs:434-454) for indices [off, off+cnt) of the full

@@ -52,6 +52,8 @@ PROTOTYPES = {
     "qvnt_reg_destroy": (c_int, [_REG]),
     "qvnt_reg_q_num": (c_int, [_REG, POINTER(c_uint32)]),
     "qvnt_reg_apply": (c_int, [_REG, POINTER(QvntOp), c_size_t]),
+    "qvnt_plan_describe": (c_int, [c_uint32, c_uint32, c_uint32, c_int, c_int, c_int, c_int, POINTER(QvntOp),
+                                   c_size_t, c_char_p, c_size_t, POINTER(c_size_t)]),
     "qvnt_reg_norm_sqr": (c_int, [_REG, POINTER(c_double)]),
     "qvnt_reg_probabilities": (c_int, [_REG, c_uint64, c_uint64, c_void_p]),
     "qvnt_reg_polar": (c_int, [_REG, c_uint64, c_uint64, c_void_p]),

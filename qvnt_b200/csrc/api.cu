@@ -353,6 +353,22 @@ int qvnt_reg_apply(qvnt_reg_t *r, const qvnt_op_t *ops, size_t n_ops) {
     return run_ops(r, ops, n_ops);
 }
 
+int qvnt_plan_describe(uint32_t q_num, uint32_t rank, uint32_t world, int peers_attached, int fuse,
+                       int tile_bits, int chunk_bits, const qvnt_op_t *ops, size_t n_ops, char *out,
+                       size_t cap, size_t *needed) {
+    if (!ops && n_ops) return QVNT_ERR_INVALID;
+    std::string s;
+    int rc = describe_plan(q_num, rank, world, peers_attached, fuse, tile_bits, chunk_bits, ops, n_ops, s);
+    if (rc) return rc;
+    if (needed) *needed = s.size() + 1;
+    if (out && cap) {
+        const size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+        memcpy(out, s.data(), n);
+        out[n] = 0;
+    }
+    return QVNT_OK;
+}
+
 int qvnt_reg_norm_sqr(qvnt_reg_t *r, double *out) {
     int rc = use(r);
     if (rc) return rc;

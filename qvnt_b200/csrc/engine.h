@@ -28,44 +28,58 @@ int launch_direct(cudaStream_t st, amp *psi, uint32_t n_local, const DevOp &op, 
                   uint64_t idx_or, uint64_t *touched_amps);
 
 // ---- fused tile pass (tile.cu) ----------------------------------------------
-constexpr int TILE_MAX_BITS = 13;
-constexpr int TILE_MAX_HIGH = 13;
+// One pass = one in-place sweep over the shard carrying MANY SingleOps.  A tile is the
+// set of 2^T amplitudes obtained by varying T "tile bits" of the global index: the low L
+// bits (one contiguous 16*2^L-byte chunk in HBM) plus T-L gathered high bits, which may be
+// rank bits of a sharded register (the chunk then lives in a peer GPU's HBM, reached over
+// NVLink through the mapped peer pointer).  The CTA stages the tile in shared memory
+// (cp.async, XOR-swizzled), runs the pass's stages on it and writes it back.
+// A stage gives every thread 2^TILE_R amplitudes in registers (TILE_R "register bits"
+// of the tile) and applies all of the stage's ops to them before touching shared memory
+// again; ops whose partner bits are not register bits wait for a later stage.
+constexpr int TILE_R = 3;
+constexpr int TILE_MAX_BITS = 12;
+constexpr int TILE_MIN_BITS = 4;
+constexpr int TILE_MAX_HIGH = 6;   // gathered (non-contiguous) tile bits: T - L <= 6
+constexpr int TILE_THREADS = 256;
 
-// Tile-local form of one op inside a pass.  Bits of the tile are numbered
-// 0..T-1 (local index j); everything outside the tile is constant per tile and
-// evaluated against the tile's base index.
-struct TileOp {
-    uint32_t kind;
-    uint32_t dagger;
-    uint32_t cls;        // OpClass
-    uint32_t mix;        // pair: local XOR mask; quad: local a bit mask
-    uint32_t mix_b;      // quad: local b bit mask
-    uint32_t pivot;      // pair: highest local bit of mix (index); quad: unused
-    uint32_t ctrl_in;    // control bits that are tile bits (local numbering)
-    uint32_t a_in;       // a_mask bits inside the tile (local numbering)
-    uint64_t ctrl_out;   // control bits outside the tile (global numbering)
-    uint64_t a_out;      // a_mask bits outside the tile (global numbering)
-    uint64_t a_glob;     // full a_mask (global numbering) -- popcount for y
-    double ph_re, ph_im;
-    uint32_t mat;        // matrix table offset
-    uint32_t sync_after; // 1: __syncthreads() needed after this op
+enum TForm : uint32_t {
+    TF_DIAG = 0,    // z/s/t/rz/rzz: no partner
+    TF_PAIR1 = 1,   // x/y/rx/ry/h1/u1 on one bit: partner = i ^ bit(ra)
+    TF_PAIR2X = 2,  // rxx/ryy: partner = i ^ bit(ra) ^ bit(rb)
+    TF_ODD2 = 3,    // swap family: odd-parity pair {bit(ra) set, bit(rb) set}
+    TF_QUAD = 4     // h2/u2: a = bit(ra), b = bit(rb)
 };
 
-struct TilePass {
-    uint32_t T;                       // tile bits
-    uint32_t chunk_bits;              // contiguous low bits of the tile (one bulk copy each)
-    uint32_t n_high;                  // T - chunk_bits gathered bits
-    uint8_t high_pos[TILE_MAX_HIGH];  // their global positions, ascending
-    // tile enumeration: counter c -> base index via Fixed (tile bits + ownership bits fixed)
-    Fixed fx;
-    uint64_t n_tiles;                 // tiles this rank processes
-    uint32_t op_begin, op_end;        // range in the pass's TileOp array
-    uint32_t touches_peer;            // some tile bit is a rank bit
+struct TOp {          // 64 bytes
+    DevOp d;          // masks in GLOBAL numbering (signs / phases / controls test the global index)
+    uint32_t form;
+    uint8_t ra, rb;   // register-bit index (0..TILE_R-1) of the op's partner bit(s)
+    uint8_t _p[2];
 };
 
-int launch_tile_pass(cudaStream_t st, const Segs &segs, const TilePass &pass, const TileOp *d_ops,
-                     const amp *mat_table, int use_tma, int sm_count);
-size_t tile_smem_bytes(uint32_t T);
+struct TStage {       // 32 bytes
+    uint32_t op_begin, op_end;   // range in the pass's TOp array
+    uint8_t r_lpos[4];           // register bit j -> tile-local bit position
+    uint8_t t_lpos[16];          // thread bit k   -> tile-local bit position (T - TILE_R entries)
+    uint32_t _pad;
+};
+
+struct TPassHdr {
+    uint32_t T, L;               // tile bits, contiguous low bits
+    uint32_t n_stages;
+    uint32_t stage_begin;        // first stage of this pass in the uploaded stage array
+    uint8_t gpos[16];            // tile-local bit -> global bit position (gpos[l] = l for l < L)
+    Fixed fx;                    // tile counter -> LOCAL base index (tile-local bits 0, ownership bits fixed)
+    uint64_t n_tiles;            // tiles this rank processes
+    uint64_t base_or;            // this rank's bits for the global qubits that are NOT tile bits
+    uint32_t touches_peer;       // some tile bit is a rank bit
+    uint32_t _pad;
+};
+
+int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, const TStage *d_stages,
+                     const TOp *d_ops, const amp *mat_table, int sm_count);
+int tile_kernel_setup();
 
 // ---- measurement / utility kernels (measure.cu) -----------------------------
 constexpr int REDUCE_BLOCKS_MAX = 4096;

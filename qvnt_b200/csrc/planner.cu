@@ -1,16 +1,21 @@
-// planner.cu -- host-side scheduler of qvnt_reg_apply: validates the op list,
-// packs runs of adjacent SingleOps into fused tile passes and enqueues the
-// kernels.  Replaces the reference's "one full out-of-place sweep per SingleOp"
-// driver: QReg::apply (src/register/quant.rs:376-395) -> MultiOp::apply
-// (src/operator/multi/mod.rs:96-114) -> SingleOp::apply (single/mod.rs:83-93).
+// planner.cu -- host-side scheduler of qvnt_reg_apply: validates the op list, packs
+// SingleOps into fused tile passes and enqueues the kernels.  Replaces the reference's
+// "one full out-of-place sweep per SingleOp" driver: QReg::apply
+// (src/register/quant.rs:376-395) -> MultiOp::apply (src/operator/multi/mod.rs:96-114)
+// -> SingleOp::apply (src/operator/single/mod.rs:83-93).
 //
-// Scheduling rule (adjacency fusion, order preserving => results identical to
-// the op-by-op order): walk the list front to back and keep extending the
-// current pass while the union of the ops' MIX bits (the bits an op XORs when it
-// gathers its partners) still fits the tile: low `chunk` bits are always in the
-// tile, at most T - chunk further bits can be gathered.  Diagonal ops and
-// control bits never constrain the tile -- outside the tile they are per-tile
-// constants.  A pass of one op that needs no peer memory runs as a direct sweep.
+// Scheduling.  Every op has MIX bits (qubits whose basis state it changes: the XOR
+// partners of its gather) and DIAGONAL bits (controls and the targets of z/s/t/rz/rzz:
+// the op is block-diagonal in them).  Two ops commute when every shared qubit is a
+// diagonal bit of both.  A pass is built greedily in list order: an op joins the pass if
+// it commutes with every earlier op that was left behind and its mix bits fit the tile
+// (low L bits are always tile bits, T-L more can be gathered -- rank bits of a sharded
+// register included, which turns the pass into the NVLink exchange).  Diagonal ops and
+// controls never constrain the tile.  Inside a pass the same greedy rule splits the ops
+// into stages by the 3 bits each thread keeps in registers.  Only the order of commuting
+// ops ever changes, so the result equals the op-by-op order up to f64 rounding
+// (|diff| ~ 1e-16, parity bar 1e-10); with option "fuse" = 0 every op is its own sweep
+// and the result is bit-identical to the reference arithmetic.
 #include <algorithm>
 #include <cstring>
 
@@ -19,14 +24,25 @@
 namespace qv {
 
 static inline int pc64(uint64_t v) { return __builtin_popcountll(v); }
+static inline int ctz64(uint64_t v) { return __builtin_ctzll(v); }
 
 struct POp {
-    DevOp d;        // masks in GLOBAL numbering, ctrl already stripped of satisfied rank bits
+    DevOp d;        // masks in GLOBAL numbering
     int cls;
-    uint64_t mix;   // bits that must lie inside a tile (0 for diagonal ops)
+    uint64_t mix;   // bits that must lie inside a tile / in registers
+    uint64_t dg;    // bits the op is diagonal in (controls, diagonal targets)
+    uint32_t src;   // index of the SingleOp in the caller's array
 };
 
-static int validate(const qvnt_reg *r, const qvnt_op_t &o, size_t k) {
+struct PlanCfg {
+    uint32_t q_num, n_local, rank, world;
+    bool peers, fuse;
+    int tile_bits, chunk_bits;
+    uint64_t q_mask() const { return q_num >= 64 ? ~0ull : ((1ull << q_num) - 1ull); }
+};
+
+static int validate(const PlanCfg &r_, const qvnt_op_t &o, size_t k) {
+    struct { uint64_t q_mask; uint32_t q_num; } rr{r_.q_mask(), r_.q_num}, *r = &rr;
     if (o.kind >= QVNT_KIND_COUNT) {
         set_error("op %zu: unknown kind %u", k, o.kind);
         return QVNT_ERR_INVALID;
@@ -57,23 +73,22 @@ static int validate(const qvnt_reg *r, const qvnt_op_t &o, size_t k) {
     return QVNT_OK;
 }
 
-int run_ops(qvnt_reg *r, const qvnt_op_t *ops, size_t n_ops) {
-    const uint64_t lmask = r->local_len - 1;
-    const uint64_t gmask = r->q_mask & ~lmask;
-    const uint64_t rbits = (uint64_t)r->rank << r->n_local;
-
-    std::vector<POp> pl;
-    pl.reserve(n_ops);
-    std::vector<amp> mats;
+// ---- lowering: qvnt_op_t -> POp ------------------------------------------------------------
+static int lower_ops(const PlanCfg &r, const qvnt_op_t *ops, size_t n_ops, std::vector<POp> &pl,
+                     std::vector<amp> &mats) {
+    const uint64_t gmask = r.q_mask() & ~((1ull << r.n_local) - 1ull);
+    const bool tile_possible = r.n_local >= (uint32_t)TILE_MIN_BITS;
+    pl.reserve(n_ops + 16);
     for (size_t k = 0; k < n_ops; ++k) {
         int rc = validate(r, ops[k], k);
         if (rc) return rc;
         const qvnt_op_t &o = ops[k];
         POp p;
         memset(&p, 0, sizeof(p));
+        p.src = (uint32_t)k;
         p.cls = op_class(o.kind);
         if (p.cls == CLS_NONE) continue;                     // Id
-        if (p.cls == CLS_PAIR && o.a_mask == 0) continue;    // x(0) / y(0): identity
+        if (p.cls == CLS_PAIR && o.a_mask == 0) continue;    // x(0) / y(0): identity (i^0)
         if (p.cls == CLS_DIAG && o.a_mask == 0 && o.kind != QVNT_RZ && o.kind != QVNT_RZZ) continue;
         p.d.kind = o.kind;
         p.d.dagger = o.dagger ? 1u : 0u;
@@ -87,47 +102,449 @@ int run_ops(qvnt_reg *r, const qvnt_op_t *ops, size_t n_ops) {
             p.d.mat = (uint32_t)mats.size();
             for (int i = 0; i < cnt; ++i) mats.push_back(make_double2(o.matrix[2 * i], o.matrix[2 * i + 1]));
         }
+        const bool split_masks = (r.fuse && tile_possible) || (o.a_mask & gmask);
+        if (split_masks && (o.kind == QVNT_X || o.kind == QVNT_Y) && pc64(o.a_mask) > 1) {
+            // x(m) = prod_b x(b), y(m) = prod_b y(b): permutations and i-power sign flips only,
+            // so the factorisation is exact (y: i^(2*ones-k), atomic/y.rs:10-23).
+            uint64_t m = o.a_mask;
+            while (m) {
+                POp q = p;
+                q.d.a = m & (~m + 1);
+                q.mix = q.d.a;
+                q.dg = q.d.ctrl;
+                pl.push_back(q);
+                m &= m - 1;
+            }
+            continue;
+        }
         p.mix = p.cls == CLS_PAIR ? p.d.a : (p.cls == CLS_QUAD ? (p.d.a | p.d.b) : 0);
+        p.dg = p.d.ctrl | (p.cls == CLS_DIAG ? p.d.a : 0);
         pl.push_back(p);
     }
-    r->stats.ops_applied += n_ops;
-    if (pl.empty()) return QVNT_OK;
+    return QVNT_OK;
+}
 
-    // matrices of u1/u2 ops -> device table
-    if (!mats.empty()) {
-        const size_t bytes = mats.size() * sizeof(amp);
-        int rc = ensure_stage(r, bytes);
-        if (rc) return rc;
-        if ((rc = ensure_dev((void **)&r->d_mat, &r->d_mat_cap, bytes))) return rc;
-        memcpy(r->h_stage, mats.data(), bytes);
-        QV_CUDA(cudaMemcpyAsync(r->d_mat, r->h_stage, bytes, cudaMemcpyHostToDevice, r->stream));
-        QV_CUDA(cudaEventRecord(r->stage_free, r->stream));
-        r->stage_busy = true;
-        r->stats.h2d_bytes += bytes;
+// ---- one direct sweep -----------------------------------------------------------------------
+static int run_direct(qvnt_reg *r, const POp &p) {
+    const uint64_t lmask = r->local_len - 1;
+    const uint64_t gmask = r->q_mask & ~lmask;
+    const uint64_t rbits = (uint64_t)r->rank << r->n_local;
+    r->stats.passes += 1;
+    if ((p.d.ctrl & gmask) & ~rbits) return QVNT_OK;     // a control on a rank bit this GPU does not satisfy
+    DevOp d = p.d;
+    d.ctrl &= lmask;
+    LaunchScope ls(r, 0);
+    uint64_t touched = 0;
+    int n = launch_direct(r->stream, r->psi, r->n_local, d, r->d_mat, rbits, &touched);
+    ls.done(n);
+    r->stats.alg_bytes[0] += touched * 32;
+    r->stats.h2d_bytes += sizeof(DevOp) + sizeof(Fixed);      // kernel parameters
+    if (n < 0) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "direct sweep launch");
+        set_error("internal: direct sweep rejected op kind %u", d.kind);
+        return QVNT_ERR_INVALID;
     }
+    return QVNT_OK;
+}
 
-    for (size_t k = 0; k < pl.size(); ++k) {
-        POp &p = pl[k];
-        if (p.mix & gmask) {
-            set_error("gate on a global (sharded) qubit needs attached peers; not available in this call path");
+// ---- pass / stage construction --------------------------------------------------------------
+struct PassPlan {
+    TPassHdr hdr;
+    std::vector<int> ops;      // indices into the POp list, in execution order
+    bool direct = false;       // single op, local: run as a direct sweep
+};
+
+// Greedy selection in list order under a bit budget.  `always` bits are free; at most
+// `budget` further bits may be added to `set`.  `allowed` = bits that may be added at all.
+// Returns the selected indices (subsequence of `cand`), and leaves the rest in `rest`.
+static void greedy_select(const std::vector<POp> &pl, const std::vector<int> &cand, uint64_t always,
+                          uint64_t allowed, int budget, uint64_t all_bits, size_t window,
+                          std::vector<int> &sel, std::vector<int> &rest, uint64_t &set_out) {
+    uint64_t set = always, bw = 0, br = 0;
+    sel.clear();
+    rest.clear();
+    size_t scanned = 0;
+    size_t i = 0;
+    for (; i < cand.size(); ++i) {
+        const POp &p = pl[cand[i]];
+        bool conflict = (p.mix & (bw | br)) || (p.dg & bw);
+        if (!conflict) {
+            const uint64_t need = p.mix & ~set;
+            if ((need & ~allowed) || pc64(need) > budget) conflict = true;
+            else {
+                set |= need;
+                budget -= pc64(need);
+                sel.push_back(cand[i]);
+            }
+        }
+        if (conflict) {
+            bw |= p.mix;
+            br |= p.dg;
+            rest.push_back(cand[i]);
+            if ((bw & all_bits) == all_bits) { ++i; break; }     // everything later is blocked
+        }
+        if (++scanned >= window && !sel.empty() && !rest.empty()) { ++i; break; }
+    }
+    for (; i < cand.size(); ++i) rest.push_back(cand[i]);
+    set_out = set;
+}
+
+struct Plan {
+    std::vector<PassPlan> passes;
+    std::vector<TStage> stages;
+    std::vector<TOp> tops;
+    std::vector<int> top_src;      // POp index of every TOp
+};
+
+// Pure host function (no CUDA): op list -> passes -> stages.
+static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) {
+    const uint32_t n_local = c.n_local;
+    const uint64_t lmask = (1ull << n_local) - 1ull;
+    const uint64_t qmask = c.q_mask();
+    const uint64_t gmask = qmask & ~lmask;
+    const bool peers = c.world > 1 && c.peers;
+    uint32_t wbits = 0;
+    while ((1u << wbits) < c.world) ++wbits;
+
+    uint32_t T = c.tile_bits ? (uint32_t)c.tile_bits : (uint32_t)TILE_MAX_BITS;
+    if (T > (uint32_t)TILE_MAX_BITS) T = TILE_MAX_BITS;
+    if (T > n_local + (peers ? wbits : 0)) T = n_local + (peers ? wbits : 0);
+    uint32_t L = c.chunk_bits ? (uint32_t)c.chunk_bits : 7u;
+    if (L > n_local) L = n_local;
+    if (L > T) L = T;
+    if (T - L > (uint32_t)TILE_MAX_HIGH) L = T - TILE_MAX_HIGH;
+    const bool tile_ok = T >= (uint32_t)TILE_MIN_BITS && n_local >= (uint32_t)TILE_MIN_BITS;
+    const uint64_t low = (1ull << L) - 1ull;
+    const uint64_t rank_bits = (uint64_t)c.rank << n_local;
+
+    std::vector<PassPlan> &passes = plan.passes;
+    std::vector<int> cand(pl.size()), sel, rest;
+    for (size_t i = 0; i < pl.size(); ++i) cand[i] = (int)i;
+    while (!cand.empty()) {
+        const POp &first = pl[cand[0]];
+        PassPlan pp;
+        memset(&pp.hdr, 0, sizeof(pp.hdr));
+        const bool first_global = (first.mix & gmask) != 0;
+        if (first_global && !peers) {
+            set_error("gate on a sharded (global) qubit needs qvnt_reg_attach_peers first");
+            return QVNT_ERR_COMM;
+        }
+        if (first_global && !tile_ok) {
+            set_error("shard too small (%u local qubits) for a global-qubit gate", n_local);
             return QVNT_ERR_UNSUPPORTED;
         }
-        // control bits on rank bits: this GPU either takes part or idles
-        const uint64_t cg = p.d.ctrl & gmask;
-        r->stats.passes += 1;
-        if (cg & ~rbits) continue;
-        DevOp d = p.d;
-        d.ctrl &= lmask;
-        LaunchScope ls(r, 0);
-        uint64_t touched = 0;
-        int n = launch_direct(r->stream, r->psi, r->n_local, d, r->d_mat, rbits, &touched);
+        if ((!c.fuse || !tile_ok) && !first_global) {
+            pp.direct = true;
+            pp.ops.push_back(cand[0]);
+            cand.erase(cand.begin());
+            passes.push_back(pp);
+            continue;
+        }
+        uint64_t set = 0;
+        const uint64_t allowed = peers ? qmask : lmask;
+        if (!c.fuse) {
+            sel.assign(1, cand[0]);
+            rest.assign(cand.begin() + 1, cand.end());
+            set = low | first.mix;
+        } else {
+            greedy_select(pl, cand, low, allowed, (int)(T - L), qmask, 1u << 16, sel, rest, set);
+        }
+        if (sel.empty()) {
+            set_error("internal: planner could not place op kind %u (mix 0x%llx) in a tile", first.d.kind,
+                      (unsigned long long)first.mix);
+            return QVNT_ERR_UNSUPPORTED;
+        }
+        if (sel.size() == 1 && !(pl[sel[0]].mix & gmask)) {
+            pp.direct = true;
+            pp.ops = sel;
+            cand.swap(rest);
+            passes.push_back(pp);
+            continue;
+        }
+        // fill the tile up to T bits with the lowest unused local bits (keeps it contiguous)
+        for (uint32_t b = L; pc64(set) < (int)T && b < n_local; ++b) set |= 1ull << b;
+        // tile-local numbering: ascending global position
+        TPassHdr &h = pp.hdr;
+        h.T = (uint32_t)pc64(set);
+        h.L = L;
+        uint32_t lp = 0;
+        for (uint64_t m = set; m; m &= m - 1) h.gpos[lp++] = (uint8_t)ctz64(m);
+        const uint64_t tile_g = set & gmask;
+        const int kg = pc64(tile_g);
+        h.touches_peer = kg ? 1u : 0u;
+        // ownership: the kg highest local non-tile bits are pinned to this rank's tile-global bits
+        uint64_t own_mask = 0, own_val = 0;
+        {
+            uint64_t tg = tile_g;
+            int b = (int)n_local - 1;
+            while (tg) {
+                while (b >= 0 && ((set >> b) & 1)) --b;
+                if (b < 0) {
+                    set_error("shard too small for a tile with %d global bits", kg);
+                    return QVNT_ERR_UNSUPPORTED;
+                }
+                const int gb = ctz64(tg);
+                own_mask |= 1ull << b;
+                if ((rank_bits >> gb) & 1ull) own_val |= 1ull << b;
+                --b;
+                tg &= tg - 1;
+            }
+        }
+        const uint64_t fixed = (set & lmask) | own_mask;
+        h.fx.n = 0;
+        h.fx._pad = 0;
+        h.fx.val = own_val;
+        for (uint64_t m = fixed; m; m &= m - 1) h.fx.pos[h.fx.n++] = (uint8_t)ctz64(m);
+        h.n_tiles = 1ull << (n_local - h.fx.n);
+        h.base_or = rank_bits & ~tile_g;
+        pp.ops = sel;
+        cand.swap(rest);
+        passes.push_back(pp);
+    }
+
+    // ---- stages of every tile pass ----
+    std::vector<TStage> &stages = plan.stages;
+    std::vector<TOp> &tops = plan.tops;
+    for (PassPlan &pp : passes) {
+        if (pp.direct) continue;
+        TPassHdr &h = pp.hdr;
+        uint64_t set = 0;
+        int lpos_of[64];
+        for (uint32_t l = 0; l < h.T; ++l) {
+            set |= 1ull << h.gpos[l];
+            lpos_of[h.gpos[l]] = (int)l;
+        }
+        h.stage_begin = (uint32_t)stages.size();
+        std::vector<int> c2 = pp.ops, s2, r2;
+        while (!c2.empty()) {
+            uint64_t rset = 0;
+            greedy_select(pl, c2, 0, set, TILE_R, set, 1u << 16, s2, r2, rset);
+            if (s2.empty()) {
+                set_error("internal: stage construction stalled");
+                return QVNT_ERR_UNSUPPORTED;
+            }
+            // register bits: the stage's mix bits + filler (highest free tile bits)
+            for (int l = (int)h.T - 1; pc64(rset) < TILE_R && l >= 0; --l) rset |= 1ull << h.gpos[l];
+            TStage st;
+            memset(&st, 0, sizeof(st));
+            int reg_of[64];
+            {
+                int j = 0;
+                for (uint64_t m = rset; m; m &= m - 1) {
+                    const int q = ctz64(m);
+                    reg_of[q] = j;
+                    st.r_lpos[j++] = (uint8_t)lpos_of[q];
+                }
+            }
+            // thread bits: lane bits 0..2 take tile-local bits congruent to 0,1,2 mod 3 so the
+            // swizzled quarter-warp access is bank-conflict free; the rest ascend
+            {
+                std::vector<int> nr;
+                for (uint32_t l = 0; l < h.T; ++l)
+                    if (!((rset >> h.gpos[l]) & 1)) nr.push_back((int)l);
+                std::vector<int> order;
+                std::vector<char> used(nr.size(), 0);
+                for (int j = 0; j < 3; ++j)
+                    for (size_t i = 0; i < nr.size(); ++i)
+                        if (!used[i] && nr[i] % 3 == j) {
+                            used[i] = 1;
+                            order.push_back(nr[i]);
+                            break;
+                        }
+                for (size_t i = 0; i < nr.size(); ++i)
+                    if (!used[i]) order.push_back(nr[i]);
+                for (size_t i = 0; i < order.size(); ++i) st.t_lpos[i] = (uint8_t)order[i];
+            }
+            st.op_begin = (uint32_t)tops.size();
+            for (int idx : s2) {
+                const POp &p = pl[idx];
+                TOp t;
+                memset(&t, 0, sizeof(t));
+                t.d = p.d;
+                if (p.cls == CLS_DIAG) t.form = TF_DIAG;
+                else if (p.cls == CLS_QUAD) {
+                    t.form = TF_QUAD;
+                    t.ra = (uint8_t)reg_of[ctz64(p.d.a)];
+                    t.rb = (uint8_t)reg_of[ctz64(p.d.b)];
+                } else if (pc64(p.d.a) == 1) {
+                    t.form = TF_PAIR1;
+                    t.ra = (uint8_t)reg_of[ctz64(p.d.a)];
+                } else {
+                    t.form = op_odd_only(p.d.kind) ? TF_ODD2 : TF_PAIR2X;
+                    const uint64_t lo = p.d.a & (~p.d.a + 1), hi = p.d.a & ~lo;
+                    t.ra = (uint8_t)reg_of[ctz64(lo)];
+                    t.rb = (uint8_t)reg_of[ctz64(hi)];
+                }
+                tops.push_back(t);
+                plan.top_src.push_back(idx);
+            }
+            st.op_end = (uint32_t)tops.size();
+            stages.push_back(st);
+            c2.swap(r2);
+        }
+        h.n_stages = (uint32_t)stages.size() - h.stage_begin;
+    }
+    return QVNT_OK;
+}
+
+static int run_plan(qvnt_reg *r, const std::vector<POp> &pl, Plan &plan) {
+    const uint32_t n_local = r->n_local;
+    // ---- upload the pass programs (one H2D copy from pinned staging) ----
+    TStage *d_stages = nullptr;
+    TOp *d_tops = nullptr;
+    if (!plan.stages.empty()) {
+        const size_t sb = plan.stages.size() * sizeof(TStage), ob = plan.tops.size() * sizeof(TOp);
+        const size_t sb_al = (sb + 255) & ~(size_t)255;
+        int rc = ensure_stage(r, sb_al + ob);
+        if (rc) return rc;
+        if ((rc = ensure_dev(&r->d_ops, &r->d_ops_cap, sb_al + ob))) return rc;
+        memcpy(r->h_stage, plan.stages.data(), sb);
+        memcpy((char *)r->h_stage + sb_al, plan.tops.data(), ob);
+        QV_CUDA(cudaMemcpyAsync(r->d_ops, r->h_stage, sb_al + ob, cudaMemcpyHostToDevice, r->stream));
+        QV_CUDA(cudaEventRecord(r->stage_free, r->stream));
+        r->stage_busy = true;
+        r->stats.h2d_bytes += sb_al + ob;
+        d_stages = (TStage *)r->d_ops;
+        d_tops = (TOp *)((char *)r->d_ops + sb_al);
+        if (tile_kernel_setup() != 0) return cuda_fail(cudaGetLastError(), "tile kernel attribute");
+    }
+
+    // ---- enqueue ----
+    bool need_barrier = false;      // peers may still be writing into / reading from this shard
+    for (PassPlan &pp : plan.passes) {
+        if (pp.direct) {
+            if (need_barrier) {
+                int rc = dist_barrier(r);
+                if (rc) return rc;
+                need_barrier = false;
+            }
+            int rc = run_direct(r, pl[pp.ops[0]]);
+            if (rc) return rc;
+            continue;
+        }
+        const TPassHdr &h = pp.hdr;
+        if (h.touches_peer || need_barrier) {
+            int rc = dist_barrier(r);
+            if (rc) return rc;
+        }
+        need_barrier = h.touches_peer != 0;
+        LaunchScope ls(r, 1);
+        int n = launch_tile_pass(r->stream, r->segs, h, d_stages, d_tops, r->d_mat, r->sm_count);
         ls.done(n);
-        r->stats.alg_bytes[0] += touched * 32;
         if (n < 0) {
             cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess) return cuda_fail(e, "direct sweep launch");
-            set_error("internal: direct sweep rejected op kind %u", d.kind);
+            if (e != cudaSuccess) return cuda_fail(e, "tile pass launch");
+            set_error("internal: tile pass rejected (T=%u L=%u)", h.T, h.L);
             return QVNT_ERR_INVALID;
+        }
+        r->stats.passes += 1;
+        r->stats.h2d_bytes += sizeof(TPassHdr) + sizeof(Segs);    // kernel parameters
+        const uint64_t amps = h.n_tiles << h.T;
+        r->stats.alg_bytes[1] += amps * 32;
+        if (h.touches_peer) {
+            int kg = 0;
+            for (uint32_t l = 0; l < h.T; ++l) kg += h.gpos[l] >= n_local;
+            r->stats.peer_bytes += ((amps * 32) >> kg) * ((1ull << kg) - 1ull);
+        }
+    }
+    if (need_barrier) {
+        int rc = dist_barrier(r);
+        if (rc) return rc;
+    }
+    return QVNT_OK;
+}
+
+static PlanCfg cfg_of(const qvnt_reg *r) {
+    PlanCfg c;
+    c.q_num = r->q_num;
+    c.n_local = r->n_local;
+    c.rank = r->rank;
+    c.world = r->world;
+    c.peers = r->peers_attached;
+    c.fuse = r->opt_fuse != 0;
+    c.tile_bits = r->opt_tile_bits;
+    c.chunk_bits = r->opt_chunk_bits;
+    return c;
+}
+
+int run_ops(qvnt_reg *r, const qvnt_op_t *ops, size_t n_ops) {
+    std::vector<POp> pl;
+    std::vector<amp> mats;
+    const PlanCfg c = cfg_of(r);
+    int rc = lower_ops(c, ops, n_ops, pl, mats);
+    if (rc) return rc;
+    r->stats.ops_applied += n_ops;
+    if (pl.empty()) return QVNT_OK;
+    Plan plan;
+    if ((rc = build_plan(c, pl, plan))) return rc;
+
+    // matrices of u1/u2 ops -> device table (pageable source: cudaMemcpyAsync stages it
+    // before returning, so `mats` may go out of scope)
+    if (!mats.empty()) {
+        const size_t bytes = mats.size() * sizeof(amp);
+        if ((rc = ensure_dev((void **)&r->d_mat, &r->d_mat_cap, bytes))) return rc;
+        QV_CUDA(cudaMemcpyAsync(r->d_mat, mats.data(), bytes, cudaMemcpyHostToDevice, r->stream));
+        r->stats.h2d_bytes += bytes;
+    }
+    return run_plan(r, pl, plan);
+}
+
+// Text dump of the schedule (tests, DESIGN.md, debugging); needs no device.
+int describe_plan(uint32_t q_num, uint32_t rank, uint32_t world, int peers, int fuse, int tile_bits,
+                  int chunk_bits, const qvnt_op_t *ops, size_t n_ops, std::string &out) {
+    PlanCfg c;
+    c.q_num = q_num;
+    c.world = world ? world : 1;
+    c.rank = rank;
+    uint32_t wb = 0;
+    while ((1u << wb) < c.world) ++wb;
+    if (q_num < wb || q_num > 40 || (c.world & (c.world - 1)) || c.world > (uint32_t)MAX_WORLD || rank >= c.world) {
+        set_error("bad register shape");
+        return QVNT_ERR_INVALID;
+    }
+    c.n_local = q_num - wb;
+    c.peers = peers != 0;
+    c.fuse = fuse != 0;
+    c.tile_bits = tile_bits;
+    c.chunk_bits = chunk_bits;
+    std::vector<POp> pl;
+    std::vector<amp> mats;
+    int rc = lower_ops(c, ops, n_ops, pl, mats);
+    if (rc) return rc;
+    Plan plan;
+    if ((rc = build_plan(c, pl, plan))) return rc;
+    char buf[512];
+    auto op_line = [&](const POp &p, int form, int ra, int rb) {
+        snprintf(buf, sizeof(buf), "op src=%u kind=%u dagger=%u a=%llu b=%llu ctrl=%llu form=%d ra=%d rb=%d\n", p.src,
+                 p.d.kind, p.d.dagger, (unsigned long long)p.d.a, (unsigned long long)p.d.b,
+                 (unsigned long long)p.d.ctrl, form, ra, rb);
+        out += buf;
+    };
+    for (const PassPlan &pp : plan.passes) {
+        if (pp.direct) {
+            out += "pass direct\n";
+            op_line(pl[pp.ops[0]], -1, -1, -1);
+            continue;
+        }
+        const TPassHdr &h = pp.hdr;
+        snprintf(buf, sizeof(buf), "pass tile T=%u L=%u n_tiles=%llu base_or=%llu peer=%u fx_val=%llu gpos=", h.T, h.L,
+                 (unsigned long long)h.n_tiles, (unsigned long long)h.base_or, h.touches_peer,
+                 (unsigned long long)h.fx.val);
+        out += buf;
+        for (uint32_t l = 0; l < h.T; ++l) out += std::to_string(h.gpos[l]) + (l + 1 < h.T ? "," : "");
+        out += " fx_pos=";
+        for (uint32_t k = 0; k < h.fx.n; ++k) out += std::to_string(h.fx.pos[k]) + (k + 1 < h.fx.n ? "," : "");
+        out += "\n";
+        for (uint32_t s = 0; s < h.n_stages; ++s) {
+            const TStage &st = plan.stages[h.stage_begin + s];
+            out += "stage r=";
+            for (int j = 0; j < TILE_R; ++j) out += std::to_string(st.r_lpos[j]) + (j + 1 < TILE_R ? "," : "");
+            out += " t=";
+            for (uint32_t k = 0; k + TILE_R < h.T; ++k) out += std::to_string(st.t_lpos[k]) + (k + 1 + TILE_R < h.T ? "," : "");
+            out += "\n";
+            for (uint32_t o = st.op_begin; o < st.op_end; ++o)
+                op_line(pl[plan.top_src[o]], (int)plan.tops[o].form, plan.tops[o].ra, plan.tops[o].rb);
         }
     }
     return QVNT_OK;

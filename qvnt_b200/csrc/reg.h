@@ -84,6 +84,8 @@ struct LaunchScope {
 
 // planner.cu: validate + schedule + enqueue one op list
 int run_ops(qvnt_reg *r, const qvnt_op_t *ops, size_t n_ops);
+int describe_plan(uint32_t q_num, uint32_t rank, uint32_t world, int peers, int fuse, int tile_bits,
+                  int chunk_bits, const qvnt_op_t *ops, size_t n_ops, std::string &out);
 // multi-GPU plumbing (dist.cu)
 int dist_barrier(qvnt_reg *r);
 int dist_allgather_double(qvnt_reg *r, double v, double *out /* world */);
