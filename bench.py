@@ -220,6 +220,8 @@ def run_ours(args):
         reg.set_option("chunk_bits", args.chunk_bits)
     if args.no_fuse:
         reg.set_option("fuse", 0)
+    if args.nbuf:
+        reg.set_option("tile_nbuf", args.nbuf)
 
     def barrier():
         if dist is not None:
@@ -339,6 +341,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--tile-bits", type=int, default=0)
+    ap.add_argument("--nbuf", type=int, default=0, help="tile buffers per CTA for T <= 11 (0 = auto)")
     ap.add_argument("--chunk-bits", type=int, default=0)
     ap.add_argument("--no-fuse", action="store_true", help="one in-place sweep per SingleOp")
     args = ap.parse_args()

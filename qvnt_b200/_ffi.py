@@ -12,7 +12,8 @@ from ctypes import POINTER, byref, c_char_p, c_double, c_int, c_int64, c_size_t,
 from .optypes import QvntOp
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqvnt_b200.so")
+# QVNT_B200_LIB selects an experimental build variant of the same library (see csrc/Makefile)
+LIB_PATH = os.environ.get("QVNT_B200_LIB") or os.path.join(_HERE, "libqvnt_b200.so")
 
 STATS_CLASSES = 5
 IPC_BLOB_BYTES = 256

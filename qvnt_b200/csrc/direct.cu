@@ -104,7 +104,7 @@ k_direct_quad(amp *__restrict__ psi, const __grid_constant__ DevOp op, const amp
     for (int u = 0; u < 2; ++u) {
         const uint64_t t = t0 + (uint64_t)u * DB;
         if (t < items) {
-            quad_update<KIND>(op, m, q[u]);
+            quad_update<KIND>(m, q[u]);
             psi[i0[u]] = q[u][0];
             psi[i0[u] | op.a] = q[u][1];
             psi[i0[u] | op.b] = q[u][2];

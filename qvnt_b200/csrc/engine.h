@@ -34,52 +34,91 @@ int launch_direct(cudaStream_t st, amp *psi, uint32_t n_local, const DevOp &op, 
 // rank bits of a sharded register (the chunk then lives in a peer GPU's HBM, reached over
 // NVLink through the mapped peer pointer).  The CTA stages the tile in shared memory
 // (cp.async, XOR-swizzled), runs the pass's stages on it and writes it back.
-// A stage gives every thread 2^TILE_R amplitudes in registers (TILE_R "register bits"
-// of the tile) and applies all of the stage's ops to them before touching shared memory
-// again; ops whose partner bits are not register bits wait for a later stage.
-constexpr int TILE_R = 3;
+// A stage gives every thread 2^TILE_R amplitudes in registers (TILE_R "register slots",
+// each holding one tile bit) and applies all of the stage's ops to them before touching
+// shared memory again; ops whose partner bits are not in register slots wait for a later
+// stage.  Everything index-dependent an op needs (controls, diagonal-phase parities) is
+// split on the host into a register-slot part (compile-time per slot), a thread part
+// (one 32-bit test per op per thread) and a tile part (one flag per op per tile), so the
+// inner loop is FP64 arithmetic plus a handful of integer instructions.
+constexpr int TILE_R = 4;
+constexpr int TILE_NV = 1 << TILE_R;
 constexpr int TILE_MAX_BITS = 12;
 constexpr int TILE_MIN_BITS = 4;
-constexpr int TILE_MAX_HIGH = 6;   // gathered (non-contiguous) tile bits: T - L <= 6
-constexpr int TILE_THREADS = 256;
+constexpr int TILE_MAX_HIGH = 8;   // gathered (non-contiguous) tile bits: T - L <= 8
+constexpr int TILE_THREADS = 256;  // = 2^(TILE_MAX_BITS - TILE_R)
+constexpr int TILE_MAX_OPS = 2048; // SingleOps per pass (their descriptors live in shared memory)
+constexpr int TILE_MAX_STAGES = 64;
 
 enum TForm : uint32_t {
     TF_DIAG = 0,    // z/s/t/rz/rzz: no partner
-    TF_PAIR1 = 1,   // x/y/rx/ry/h1/u1 on one bit: partner = i ^ bit(ra)
-    TF_PAIR2X = 2,  // rxx/ryy: partner = i ^ bit(ra) ^ bit(rb)
-    TF_ODD2 = 3,    // swap family: odd-parity pair {bit(ra) set, bit(rb) set}
-    TF_QUAD = 4     // h2/u2: a = bit(ra), b = bit(rb)
+    TF_PAIR1 = 1,   // x/y/rx/ry/h1/u1 on one bit: partner differs in slot ra
+    TF_PAIR2X = 2,  // rxx/ryy: partner differs in slots ra and rb
+    TF_ODD2 = 3,    // swap family: odd-parity pair {slot ra set, slot rb set}
+    TF_QUAD = 4     // h2/u2: a = slot ra, b = slot rb
 };
 
-struct TOp {          // 64 bytes
-    DevOp d;          // masks in GLOBAL numbering (signs / phases / controls test the global index)
-    uint32_t form;
-    uint8_t ra, rb;   // register-bit index (0..TILE_R-1) of the op's partner bit(s)
-    uint8_t _p[2];
+// Dispatch codes of the stage interpreter (tile.cu).  Two-bit ops sit on the slot pairs
+// (0,1) or (2,3) only; the planner assigns slots accordingly.
+enum MCode : uint8_t {
+    MC_DU = 0,    // + {Z,S,T,RZ,RZZ}: diagonal, no target bit in a register slot (one factor per thread)
+    MC_DG = 5,    // + {Z,S,T,RZ,RZZ}: diagonal, per-slot factor
+    MC_P1 = 10,   // + 4*{X,Y,RX,RY,H1,U1} + slot
+    MC_P2X = 34,  // + 2*{RXX,RYY} + pair
+    MC_ODD = 38,  // + 2*{SWAP,ISWAP,SQRT_SWAP,SQRT_ISWAP} + pair
+    MC_H2 = 46,   // + pair
+    MC_U2 = 48,   // + 2*pair + (a sits in the odd slot)
+    MC_COUNT = 52
+};
+
+struct __align__(16) MOp {   // 32 bytes, staged in shared memory
+    uint8_t code;        // MCode
+    uint8_t dagger;
+    uint16_t okmask;     // bit K: register slot pattern K satisfies the controls held in register slots
+    uint32_t ctrl_thr;   // controls on thread bits (bit k = thread bit k of the stage)
+    uint32_t a_thr;      // diagonal class: target-mask bits on thread bits; u1/u2: matrix table index
+    uint16_t a_reg;      // diagonal class: target-mask bits on register slots
+    uint16_t _pad;
+    double ph_re, ph_im;
+};
+static_assert(sizeof(MOp) == 32, "MOp layout");
+
+struct MBase {           // per-op masks over the index bits that are NOT tile bits (global numbering)
+    uint64_t ctrl_base;
+    uint64_t a_base;     // diagonal class only
 };
 
 struct TStage {       // 32 bytes
-    uint32_t op_begin, op_end;   // range in the pass's TOp array
-    uint8_t r_lpos[4];           // register bit j -> tile-local bit position
-    uint8_t t_lpos[16];          // thread bit k   -> tile-local bit position (T - TILE_R entries)
+    uint32_t op_begin, op_end;   // range in the uploaded MOp array
+    uint8_t r_lpos[4];           // register slot j -> tile-local bit position
+    uint8_t t_lpos[16];          // thread bit k    -> tile-local bit position (T - TILE_R entries)
     uint32_t _pad;
 };
+static_assert(sizeof(TStage) == 32, "TStage layout");
 
 struct TPassHdr {
     uint32_t T, L;               // tile bits, contiguous low bits
     uint32_t n_stages;
     uint32_t stage_begin;        // first stage of this pass in the uploaded stage array
+    uint32_t op_begin, n_ops;    // this pass's ops in the uploaded MOp / MBase arrays
     uint8_t gpos[16];            // tile-local bit -> global bit position (gpos[l] = l for l < L)
-    Fixed fx;                    // tile counter -> LOCAL base index (tile-local bits 0, ownership bits fixed)
+    // tile counter -> LOCAL base index (tile-local bits 0, ownership bits fixed): runs of
+    // fixed positions, ascending; base = expand(counter) | fx_val
+    uint32_t n_runs;
+    uint8_t run_pos[16], run_len[16];
+    uint64_t fx_val;
     uint64_t n_tiles;            // tiles this rank processes
     uint64_t base_or;            // this rank's bits for the global qubits that are NOT tile bits
     uint32_t touches_peer;       // some tile bit is a rank bit
-    uint32_t _pad;
+    uint32_t full;               // some op needs the full interpreter (u1/u2, two-bit pair ops, h2)
+    uint16_t stage_end[TILE_MAX_STAGES];   // ops of stage s: [stage_end[s-1], stage_end[s]) relative to op_begin
+    Fixed fx;                    // the same enumeration bit by bit (host side: describe / tests)
 };
 
 int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, const TStage *d_stages,
-                     const TOp *d_ops, const amp *mat_table, int sm_count);
+                     const MOp *d_ops, const MBase *d_bases, const amp *mat_table, int sm_count);
 int tile_kernel_setup();
+extern int g_tile_nbuf;
 
 // ---- measurement / utility kernels (measure.cu) -----------------------------
 constexpr int REDUCE_BLOCKS_MAX = 4096;

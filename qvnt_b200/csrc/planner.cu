@@ -12,7 +12,7 @@
 // (low L bits are always tile bits, T-L more can be gathered -- rank bits of a sharded
 // register included, which turns the pass into the NVLink exchange).  Diagonal ops and
 // controls never constrain the tile.  Inside a pass the same greedy rule splits the ops
-// into stages by the 3 bits each thread keeps in registers.  Only the order of commuting
+// into stages by the TILE_R bits each thread keeps in registers.  Only the order of commuting
 // ops ever changes, so the result equals the op-by-op order up to f64 rounding
 // (|diff| ~ 1e-16, parity bar 1e-10); with option "fuse" = 0 every op is its own sweep
 // and the result is bit-identical to the reference arithmetic.
@@ -190,12 +190,113 @@ static void greedy_select(const std::vector<POp> &pl, const std::vector<int> &ca
     set_out = set;
 }
 
+struct MInfo { int src; int form, ra, rb; };   // host-side description of every MOp (describe / tests)
+
 struct Plan {
     std::vector<PassPlan> passes;
     std::vector<TStage> stages;
-    std::vector<TOp> tops;
-    std::vector<int> top_src;      // POp index of every TOp
+    std::vector<MOp> mops;
+    std::vector<MBase> bases;
+    std::vector<MInfo> minfo;
 };
+
+// ---- stage selection: which ops run while WHICH tile bits sit in the register slots ----------
+// Greedy in list order like greedy_select, but with slot placement: one-bit ops take any
+// slot, two-bit ops (rxx/ryy, swap family, h2/u2) must sit on the slot pair (0,1) or (2,3)
+// because the interpreter only carries bodies for those (tile.cu).
+struct Slots {
+    int bit[TILE_R];     // global bit held by slot j, -1 = free
+    int find(int q) const {
+        for (int j = 0; j < TILE_R; ++j)
+            if (bit[j] == q) return j;
+        return -1;
+    }
+};
+
+static bool place_op(const POp &p, Slots &sl, int &ra, int &rb) {
+    ra = rb = 0;
+    if (p.mix == 0) return true;
+    if (pc64(p.mix) == 1) {
+        const int q = ctz64(p.mix);
+        int j = sl.find(q);
+        if (j < 0) {
+            // prefer a free slot whose pair partner is already taken (keeps whole pairs free)
+            for (int k = TILE_R - 1; k >= 0 && j < 0; --k)
+                if (sl.bit[k] < 0 && sl.bit[k ^ 1] >= 0) j = k;
+            for (int k = TILE_R - 1; k >= 0 && j < 0; --k)
+                if (sl.bit[k] < 0) j = k;
+            if (j < 0) return false;
+            sl.bit[j] = q;
+        }
+        ra = j;
+        return true;
+    }
+    // two mix bits: x = a (or the lower bit of ab), y = b (or the upper bit)
+    int x, y;
+    if (p.cls == CLS_QUAD) {
+        x = ctz64(p.d.a);
+        y = ctz64(p.d.b);
+    } else {
+        x = ctz64(p.mix);
+        y = ctz64(p.mix & (p.mix - 1));
+    }
+    int jx = sl.find(x), jy = sl.find(y);
+    if (jx >= 0 && jy >= 0) {
+        if ((jx ^ jy) != 1) return false;
+    } else if (jx >= 0) {
+        if (sl.bit[jx ^ 1] >= 0) return false;
+        jy = jx ^ 1;
+        sl.bit[jy] = y;
+    } else if (jy >= 0) {
+        if (sl.bit[jy ^ 1] >= 0) return false;
+        jx = jy ^ 1;
+        sl.bit[jx] = x;
+    } else {
+        int pr = -1;
+        for (int k = 0; k + 1 < TILE_R; k += 2)
+            if (sl.bit[k] < 0 && sl.bit[k + 1] < 0) pr = k;
+        if (pr < 0) return false;
+        jx = pr;
+        jy = pr + 1;
+        sl.bit[jx] = x;
+        sl.bit[jy] = y;
+    }
+    ra = jx;
+    rb = jy;
+    return true;
+}
+
+struct StageSel { int idx, ra, rb; };
+
+static void stage_select(const std::vector<POp> &pl, const std::vector<int> &cand, uint64_t tile_set,
+                         size_t max_ops, std::vector<StageSel> &sel, std::vector<int> &rest, Slots &sl) {
+    for (int j = 0; j < TILE_R; ++j) sl.bit[j] = -1;
+    uint64_t bw = 0, br = 0;
+    sel.clear();
+    rest.clear();
+    size_t i = 0;
+    for (; i < cand.size(); ++i) {
+        const POp &p = pl[cand[i]];
+        bool conflict = (p.mix & (bw | br)) || (p.dg & bw) || sel.size() >= max_ops;
+        if (!conflict) {
+            Slots trial = sl;
+            int ra, rb;
+            if (place_op(p, trial, ra, rb)) {
+                sl = trial;
+                sel.push_back({cand[i], ra, rb});
+            } else {
+                conflict = true;
+            }
+        }
+        if (conflict) {
+            bw |= p.mix;
+            br |= p.dg;
+            rest.push_back(cand[i]);
+            if ((bw & tile_set) == tile_set) { ++i; break; }     // everything later is blocked
+        }
+    }
+    for (; i < cand.size(); ++i) rest.push_back(cand[i]);
+}
 
 // Pure host function (no CUDA): op list -> passes -> stages.
 static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) {
@@ -304,10 +405,12 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
     }
 
     // ---- stages of every tile pass ----
-    std::vector<TStage> &stages = plan.stages;
-    std::vector<TOp> &tops = plan.tops;
+    std::vector<PassPlan> out_passes;
     for (PassPlan &pp : passes) {
-        if (pp.direct) continue;
+        if (pp.direct) {
+            out_passes.push_back(pp);
+            continue;
+        }
         TPassHdr &h = pp.hdr;
         uint64_t set = 0;
         int lpos_of[64];
@@ -315,35 +418,74 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
             set |= 1ull << h.gpos[l];
             lpos_of[h.gpos[l]] = (int)l;
         }
-        h.stage_begin = (uint32_t)stages.size();
-        std::vector<int> c2 = pp.ops, s2, r2;
-        while (!c2.empty()) {
-            uint64_t rset = 0;
-            greedy_select(pl, c2, 0, set, TILE_R, set, 1u << 16, s2, r2, rset);
-            if (s2.empty()) {
-                set_error("internal: stage construction stalled");
+        // runs of fixed positions for the kernel's tile-counter expansion
+        h.n_runs = 0;
+        for (uint32_t k = 0; k < h.fx.n;) {
+            uint32_t e = k + 1;
+            while (e < h.fx.n && h.fx.pos[e] == h.fx.pos[e - 1] + 1) ++e;
+            if (h.n_runs >= 16) {
+                set_error("internal: tile geometry needs more than 16 runs");
                 return QVNT_ERR_UNSUPPORTED;
             }
-            // register bits: the stage's mix bits + filler (highest free tile bits)
-            for (int l = (int)h.T - 1; pc64(rset) < TILE_R && l >= 0; --l) rset |= 1ull << h.gpos[l];
+            h.run_pos[h.n_runs] = h.fx.pos[k];
+            h.run_len[h.n_runs] = (uint8_t)(e - k);
+            ++h.n_runs;
+            k = e;
+        }
+        h.fx_val = h.fx.val;
+
+        PassPlan cur = pp;           // same geometry; ops / stages filled below (split if too long)
+        cur.ops.clear();
+        cur.hdr.stage_begin = (uint32_t)plan.stages.size();
+        cur.hdr.op_begin = (uint32_t)plan.mops.size();
+        auto flush = [&]() {
+            cur.hdr.n_stages = (uint32_t)plan.stages.size() - cur.hdr.stage_begin;
+            cur.hdr.n_ops = (uint32_t)plan.mops.size() - cur.hdr.op_begin;
+            for (uint32_t k = 0; k < cur.hdr.n_stages; ++k)
+                cur.hdr.stage_end[k] = (uint16_t)(plan.stages[cur.hdr.stage_begin + k].op_end - cur.hdr.op_begin);
+            if (cur.hdr.n_ops) out_passes.push_back(cur);
+            cur.ops.clear();
+            cur.hdr.full = 0;
+            cur.hdr.stage_begin = (uint32_t)plan.stages.size();
+            cur.hdr.op_begin = (uint32_t)plan.mops.size();
+        };
+        std::vector<int> c2 = pp.ops, r2;
+        std::vector<StageSel> s2;
+        while (!c2.empty()) {
+            Slots sl;
+            const size_t room = (size_t)TILE_MAX_OPS - (plan.mops.size() - cur.hdr.op_begin);
+            stage_select(pl, c2, set, room, s2, r2, sl);
+            if (s2.empty() || plan.stages.size() - cur.hdr.stage_begin >= (size_t)TILE_MAX_STAGES) {
+                if (plan.mops.size() == cur.hdr.op_begin) {
+                    set_error("internal: stage construction stalled");
+                    return QVNT_ERR_UNSUPPORTED;
+                }
+                flush();               // program full: continue in a new pass over the same tiles
+                continue;
+            }
+            // register slots: the stage's mix bits + filler (highest free tile bits)
+            uint64_t rset = 0;
+            for (int j = 0; j < TILE_R; ++j)
+                if (sl.bit[j] >= 0) rset |= 1ull << sl.bit[j];
+            for (int j = 0; j < TILE_R; ++j) {
+                if (sl.bit[j] >= 0) continue;
+                for (int l = (int)h.T - 1; l >= 0; --l)
+                    if (!((rset >> h.gpos[l]) & 1)) {
+                        sl.bit[j] = h.gpos[l];
+                        rset |= 1ull << h.gpos[l];
+                        break;
+                    }
+            }
             TStage st;
             memset(&st, 0, sizeof(st));
-            int reg_of[64];
-            {
-                int j = 0;
-                for (uint64_t m = rset; m; m &= m - 1) {
-                    const int q = ctz64(m);
-                    reg_of[q] = j;
-                    st.r_lpos[j++] = (uint8_t)lpos_of[q];
-                }
-            }
+            for (int j = 0; j < TILE_R; ++j) st.r_lpos[j] = (uint8_t)lpos_of[sl.bit[j]];
             // thread bits: lane bits 0..2 take tile-local bits congruent to 0,1,2 mod 3 so the
             // swizzled quarter-warp access is bank-conflict free; the rest ascend
+            std::vector<int> order;
             {
                 std::vector<int> nr;
                 for (uint32_t l = 0; l < h.T; ++l)
                     if (!((rset >> h.gpos[l]) & 1)) nr.push_back((int)l);
-                std::vector<int> order;
                 std::vector<char> used(nr.size(), 0);
                 for (int j = 0; j < 3; ++j)
                     for (size_t i = 0; i < nr.size(); ++i)
@@ -356,35 +498,100 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                     if (!used[i]) order.push_back(nr[i]);
                 for (size_t i = 0; i < order.size(); ++i) st.t_lpos[i] = (uint8_t)order[i];
             }
-            st.op_begin = (uint32_t)tops.size();
-            for (int idx : s2) {
-                const POp &p = pl[idx];
-                TOp t;
-                memset(&t, 0, sizeof(t));
-                t.d = p.d;
-                if (p.cls == CLS_DIAG) t.form = TF_DIAG;
-                else if (p.cls == CLS_QUAD) {
-                    t.form = TF_QUAD;
-                    t.ra = (uint8_t)reg_of[ctz64(p.d.a)];
-                    t.rb = (uint8_t)reg_of[ctz64(p.d.b)];
+            // index-bit classes of this stage, in global numbering
+            uint64_t reg_of_bit[TILE_R];
+            for (int j = 0; j < TILE_R; ++j) reg_of_bit[j] = 1ull << sl.bit[j];
+            auto split = [&](uint64_t m, uint32_t &reg, uint32_t &thr, uint64_t &base) {
+                reg = thr = 0;
+                for (int j = 0; j < TILE_R; ++j)
+                    if (m & reg_of_bit[j]) reg |= 1u << j;
+                for (size_t k = 0; k < order.size(); ++k)
+                    if ((m >> h.gpos[order[k]]) & 1ull) thr |= 1u << k;
+                base = m & ~set;
+            };
+            st.op_begin = (uint32_t)plan.mops.size();
+            for (const StageSel &ss : s2) {
+                const POp &p = pl[ss.idx];
+                MOp m;
+                MBase b;
+                MInfo mi;
+                memset(&m, 0, sizeof(m));
+                memset(&b, 0, sizeof(b));
+                uint32_t creg, cthr;
+                split(p.d.ctrl, creg, cthr, b.ctrl_base);
+                m.ctrl_thr = cthr;
+                m.okmask = 0;
+                for (int K = 0; K < TILE_NV; ++K)
+                    if ((~(uint32_t)K & creg) == 0) m.okmask |= (uint16_t)(1u << K);
+                m.dagger = (uint8_t)p.d.dagger;
+                m.ph_re = p.d.ph_re;
+                m.ph_im = p.d.ph_im;
+                mi.src = ss.idx;
+                mi.ra = ss.ra;
+                mi.rb = ss.rb;
+                if (p.cls == CLS_DIAG) {
+                    uint32_t areg, athr;
+                    split(p.d.a, areg, athr, b.a_base);
+                    m.a_reg = (uint16_t)areg;
+                    m.a_thr = athr;
+                    int k5 = p.d.kind == QVNT_Z ? 0 : p.d.kind == QVNT_S ? 1 : p.d.kind == QVNT_T ? 2
+                             : p.d.kind == QVNT_RZ ? 3 : 4;
+                    m.code = (uint8_t)((areg ? MC_DG : MC_DU) + k5);
+                    mi.form = TF_DIAG;
+                    mi.ra = mi.rb = 0;
+                } else if (p.cls == CLS_QUAD) {
+                    mi.form = TF_QUAD;
+                    const int pair = ss.ra >> 1;
+                    if (p.d.kind == QVNT_H2) m.code = (uint8_t)(MC_H2 + pair);
+                    else {
+                        m.code = (uint8_t)(MC_U2 + 2 * pair + (ss.ra & 1));
+                        m.a_thr = p.d.mat;
+                    }
                 } else if (pc64(p.d.a) == 1) {
-                    t.form = TF_PAIR1;
-                    t.ra = (uint8_t)reg_of[ctz64(p.d.a)];
+                    mi.form = TF_PAIR1;
+                    int k6;
+                    switch (p.d.kind) {
+                    case QVNT_X: k6 = 0; break;
+                    case QVNT_Y: k6 = 1; break;
+                    case QVNT_RX: k6 = 2; break;
+                    case QVNT_RY: k6 = 3; break;
+                    case QVNT_H1: k6 = 4; break;
+                    case QVNT_U1: k6 = 5; break;
+                    default:
+                        set_error("internal: kind %u is not a one-bit pair op", p.d.kind);
+                        return QVNT_ERR_INVALID;
+                    }
+                    m.code = (uint8_t)(MC_P1 + 4 * k6 + ss.ra);
+                    if (p.d.kind == QVNT_U1) m.a_thr = p.d.mat;
                 } else {
-                    t.form = op_odd_only(p.d.kind) ? TF_ODD2 : TF_PAIR2X;
-                    const uint64_t lo = p.d.a & (~p.d.a + 1), hi = p.d.a & ~lo;
-                    t.ra = (uint8_t)reg_of[ctz64(lo)];
-                    t.rb = (uint8_t)reg_of[ctz64(hi)];
+                    const int pair = ss.ra >> 1;
+                    if (op_odd_only(p.d.kind)) {
+                        mi.form = TF_ODD2;
+                        const int k4 = p.d.kind == QVNT_SWAP ? 0 : p.d.kind == QVNT_ISWAP ? 1
+                                       : p.d.kind == QVNT_SQRT_SWAP ? 2 : 3;
+                        m.code = (uint8_t)(MC_ODD + 2 * k4 + pair);
+                    } else if (p.d.kind == QVNT_RXX || p.d.kind == QVNT_RYY) {
+                        mi.form = TF_PAIR2X;
+                        m.code = (uint8_t)(MC_P2X + 2 * (p.d.kind == QVNT_RYY) + pair);
+                    } else {
+                        set_error("internal: kind %u with a %d-bit mask reached the tile planner", p.d.kind,
+                                  pc64(p.d.a));
+                        return QVNT_ERR_INVALID;
+                    }
                 }
-                tops.push_back(t);
-                plan.top_src.push_back(idx);
+                if (m.code >= MC_P1 + 20) cur.hdr.full = 1;      // u1 and everything after it in MCode
+                plan.mops.push_back(m);
+                plan.bases.push_back(b);
+                plan.minfo.push_back(mi);
+                cur.ops.push_back(ss.idx);
             }
-            st.op_end = (uint32_t)tops.size();
-            stages.push_back(st);
+            st.op_end = (uint32_t)plan.mops.size();
+            plan.stages.push_back(st);
             c2.swap(r2);
         }
-        h.n_stages = (uint32_t)stages.size() - h.stage_begin;
+        flush();
     }
+    passes.swap(out_passes);
     return QVNT_OK;
 }
 
@@ -392,21 +599,26 @@ static int run_plan(qvnt_reg *r, const std::vector<POp> &pl, Plan &plan) {
     const uint32_t n_local = r->n_local;
     // ---- upload the pass programs (one H2D copy from pinned staging) ----
     TStage *d_stages = nullptr;
-    TOp *d_tops = nullptr;
+    MOp *d_mops = nullptr;
+    MBase *d_bases = nullptr;
     if (!plan.stages.empty()) {
-        const size_t sb = plan.stages.size() * sizeof(TStage), ob = plan.tops.size() * sizeof(TOp);
-        const size_t sb_al = (sb + 255) & ~(size_t)255;
-        int rc = ensure_stage(r, sb_al + ob);
+        const size_t sb = plan.stages.size() * sizeof(TStage), ob = plan.mops.size() * sizeof(MOp),
+                     bb = plan.bases.size() * sizeof(MBase);
+        const size_t sb_al = (sb + 255) & ~(size_t)255, ob_al = (ob + 255) & ~(size_t)255;
+        const size_t total = sb_al + ob_al + bb;
+        int rc = ensure_stage(r, total);
         if (rc) return rc;
-        if ((rc = ensure_dev(&r->d_ops, &r->d_ops_cap, sb_al + ob))) return rc;
+        if ((rc = ensure_dev(&r->d_ops, &r->d_ops_cap, total))) return rc;
         memcpy(r->h_stage, plan.stages.data(), sb);
-        memcpy((char *)r->h_stage + sb_al, plan.tops.data(), ob);
-        QV_CUDA(cudaMemcpyAsync(r->d_ops, r->h_stage, sb_al + ob, cudaMemcpyHostToDevice, r->stream));
+        memcpy((char *)r->h_stage + sb_al, plan.mops.data(), ob);
+        memcpy((char *)r->h_stage + sb_al + ob_al, plan.bases.data(), bb);
+        QV_CUDA(cudaMemcpyAsync(r->d_ops, r->h_stage, total, cudaMemcpyHostToDevice, r->stream));
         QV_CUDA(cudaEventRecord(r->stage_free, r->stream));
         r->stage_busy = true;
-        r->stats.h2d_bytes += sb_al + ob;
+        r->stats.h2d_bytes += total;
         d_stages = (TStage *)r->d_ops;
-        d_tops = (TOp *)((char *)r->d_ops + sb_al);
+        d_mops = (MOp *)((char *)r->d_ops + sb_al);
+        d_bases = (MBase *)((char *)r->d_ops + sb_al + ob_al);
         if (tile_kernel_setup() != 0) return cuda_fail(cudaGetLastError(), "tile kernel attribute");
     }
 
@@ -430,7 +642,7 @@ static int run_plan(qvnt_reg *r, const std::vector<POp> &pl, Plan &plan) {
         }
         need_barrier = h.touches_peer != 0;
         LaunchScope ls(r, 1);
-        int n = launch_tile_pass(r->stream, r->segs, h, d_stages, d_tops, r->d_mat, r->sm_count);
+        int n = launch_tile_pass(r->stream, r->segs, h, d_stages, d_mops, d_bases, r->d_mat, r->sm_count);
         ls.done(n);
         if (n < 0) {
             cudaError_t e = cudaGetLastError();
@@ -544,7 +756,7 @@ int describe_plan(uint32_t q_num, uint32_t rank, uint32_t world, int peers, int 
             for (uint32_t k = 0; k + TILE_R < h.T; ++k) out += std::to_string(st.t_lpos[k]) + (k + 1 + TILE_R < h.T ? "," : "");
             out += "\n";
             for (uint32_t o = st.op_begin; o < st.op_end; ++o)
-                op_line(pl[plan.top_src[o]], (int)plan.tops[o].form, plan.tops[o].ra, plan.tops[o].rb);
+                op_line(pl[plan.minfo[o].src], plan.minfo[o].form, plan.minfo[o].ra, plan.minfo[o].rb);
         }
     }
     return QVNT_OK;

@@ -15,8 +15,21 @@
 // exchange step -- the "swap" is the tile's own load and store.
 //
 // Shared memory is XOR-swizzled at 16-byte granularity (slot ^= fold of the upper index
-// bits into the low 3) so that, whichever 3 bits a stage keeps in registers, the 8 lanes
+// bits into the low 3) so that, whichever bits a stage keeps in registers, the 8 lanes
 // of a quarter-warp hit 8 different 16-byte bank groups (the planner picks the lane bits).
+// The swizzle is GF(2)-linear, so a thread's 16 slot addresses are one base XOR 16
+// stage-uniform constants.
+//
+// The stage interpreter.  A stage keeps TILE_R = 4 tile bits in "register slots": every
+// thread holds the 16 amplitudes that differ in those bits.  An op is a 32-byte MOp in
+// shared memory whose `code` selects a fully unrolled body (kind x slot); everything
+// that depends on the amplitude index was split by the planner into
+//   - register-slot part: compile-time per slot (signs of ry/h1/y/ryy, rows of u1/u2) or a
+//     16-bit `okmask` (controls sitting in register slots),
+//   - thread part: one AND/compare on the thread's group number per op,
+//   - tile part: one flag byte per op per tile (controls / diagonal-mask bits outside the
+//     tile), computed once per tile.
+// Tiles none of whose ops is active (multi-controlled gates) are skipped without being read.
 //
 // Arithmetic: every gate uses the reference's formula (gates.cuh) with FMA contraction
 // off, on the same operands as the reference's gather form; only the ORDER of commuting
@@ -25,6 +38,12 @@
 #include "gates.cuh"
 
 namespace qv {
+
+#ifndef QV_OP_PREFETCH
+#define QV_OP_PREFETCH 0
+#endif
+constexpr int NV = TILE_NV;
+constexpr int TR = TILE_R;
 
 __device__ __forceinline__ uint32_t swz(uint32_t j) {
     return j ^ (((j >> 3) ^ (j >> 6) ^ (j >> 9)) & 7u);
@@ -38,328 +57,478 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-// global index of register slot K of a thread whose register bits are all clear in g
-template <int K>
-__device__ __forceinline__ uint64_t gi(uint64_t g, const uint64_t (&rg)[TILE_R]) {
-    uint64_t i = g;
-    if (K & 1) i |= rg[0];
-    if (K & 2) i |= rg[1];
-    if (K & 4) i |= rg[2];
-    return i;
-}
+// ---- op bodies: templated on kind and register slot(s), fully unrolled over the 16 slots -----
+#define QV_FOR_K _Pragma("unroll") for (int K = 0; K < NV; ++K)
+// Controls held in register slots are warp-uniform (okmask comes from the op descriptor): keep
+// them as real branches -- the empty volatile asm stops the compiler from if-converting the
+// guarded update into "compute both, then 4 selects per amplitude".
+#define QV_GUARD(ALL) do { if (!(ALL)) asm volatile(""); } while (0)
 
-template <int K, int END, typename F>
-struct StaticFor {
-    static __device__ __forceinline__ void run(F &f) {
-        f.template operator()<K>();
-        StaticFor<K + 1, END, F>::run(f);
-    }
-};
-template <int END, typename F>
-struct StaticFor<END, END, F> {
-    static __device__ __forceinline__ void run(F &) {}
-};
+// one-bit pair ops (x/y/rx/ry/h1/u1) on register slot RB
+// The 8 pair updates of an op run as two halves separated by an always-taken branch the
+// compiler cannot fold (gridDim.y == 1): ptxas schedules inside basic blocks, so at most 4 pairs'
+// products are in flight at once -- enough to fill the FP64 pipe, and ~20 registers fewer than
+// the full interleave, which is what keeps the interpreter's loop state out of local memory.
+#define QV_HALF_SPLIT (gridDim.y == 1u)
 
-constexpr int NV = 1 << TILE_R;
-
-// ---- per-form bodies, templated on the gate kind and the register bits involved ---------
-template <int KIND>
-struct DiagBody {
-    const DevOp &d;
-    amp (&v)[NV];
-    uint64_t g;
-    const uint64_t (&rg)[TILE_R];
-    template <int K>
-    __device__ __forceinline__ void operator()() {
-        const uint64_t i = gi<K>(g, rg);
-        if ((~i & d.ctrl) == 0) v[K] = diag_out<KIND>(d, v[K], i);
-    }
-};
-
-template <int KIND, int RB>
-struct Pair1Body {
-    const DevOp &d;
-    const amp *m;
-    amp (&v)[NV];
-    uint64_t g;
-    const uint64_t (&rg)[TILE_R];
-    template <int K>
-    __device__ __forceinline__ void operator()() {
-        if (K & (1 << RB)) return;
-        constexpr int K1 = K | (1 << RB);
-        const uint64_t i0 = gi<K>(g, rg), i1 = gi<K1>(g, rg);
-        if ((~i0 & d.ctrl) == 0) pair_update<KIND>(d, m, v[K], v[K1], i0, i1);
-    }
-};
-
-template <int KIND, int RA, int RB>
-struct Pair2XBody {   // partner differs in both register bits
-    const DevOp &d;
-    const amp *m;
-    amp (&v)[NV];
-    uint64_t g;
-    const uint64_t (&rg)[TILE_R];
-    template <int K>
-    __device__ __forceinline__ void operator()() {
-        if (K & (1 << RA)) return;
-        constexpr int K1 = K ^ (1 << RA) ^ (1 << RB);
-        const uint64_t i0 = gi<K>(g, rg), i1 = gi<K1>(g, rg);
-        if ((~i0 & d.ctrl) == 0) pair_update<KIND>(d, m, v[K], v[K1], i0, i1);
-    }
-};
-
-template <int KIND, int RA, int RB>
-struct Odd2Body {     // swap family: only the odd-parity pair {a set, b set} changes
-    const DevOp &d;
-    const amp *m;
-    amp (&v)[NV];
-    uint64_t g;
-    const uint64_t (&rg)[TILE_R];
-    template <int K>
-    __device__ __forceinline__ void operator()() {
-        if (K & ((1 << RA) | (1 << RB))) return;
-        constexpr int K0 = K | (1 << RA), K1 = K | (1 << RB);
-        const uint64_t i0 = gi<K0>(g, rg), i1 = gi<K1>(g, rg);
-        if ((~i0 & d.ctrl) == 0) pair_update<KIND>(d, m, v[K0], v[K1], i0, i1);
-    }
-};
-
-template <int KIND, int RA, int RB>
-struct QuadBody {     // h2 / u2: a = register bit RA, b = register bit RB
-    const DevOp &d;
-    const amp *m;
-    amp (&v)[NV];
-    uint64_t g;
-    const uint64_t (&rg)[TILE_R];
-    template <int K>
-    __device__ __forceinline__ void operator()() {
-        if (K & ((1 << RA) | (1 << RB))) return;
-        const uint64_t i0 = gi<K>(g, rg);
-        if ((~i0 & d.ctrl) != 0) return;
-        amp q[4] = {v[K], v[K | (1 << RA)], v[K | (1 << RB)], v[K | (1 << RA) | (1 << RB)]};
-        quad_update<KIND>(d, m, q);
-        v[K] = q[0];
-        v[K | (1 << RA)] = q[1];
-        v[K | (1 << RB)] = q[2];
-        v[K | (1 << RA) | (1 << RB)] = q[3];
-    }
-};
-
-#define COMMA ,
-#define QV_RUN(BODY)                                   \
-    do {                                               \
-        BODY body_{d, m, v, g, rg};                    \
-        StaticFor<0, NV, BODY>::run(body_);            \
-    } while (0)
-#define QV_RUN_D(BODY)                                 \
-    do {                                               \
-        BODY body_{d, v, g, rg};                       \
-        StaticFor<0, NV, BODY>::run(body_);            \
-    } while (0)
-
-template <int RB>
-__device__ __forceinline__ void run_pair1(const DevOp &d, const amp *m, amp (&v)[NV], uint64_t g,
-                                          const uint64_t (&rg)[TILE_R]) {
-    switch (d.kind) {
-    case QVNT_X: QV_RUN(Pair1Body<QVNT_X COMMA RB>); break;
-    case QVNT_Y: QV_RUN(Pair1Body<QVNT_Y COMMA RB>); break;
-    case QVNT_RX: QV_RUN(Pair1Body<QVNT_RX COMMA RB>); break;
-    case QVNT_RY: QV_RUN(Pair1Body<QVNT_RY COMMA RB>); break;
-    case QVNT_H1: QV_RUN(Pair1Body<QVNT_H1 COMMA RB>); break;
-    default: QV_RUN(Pair1Body<QVNT_U1 COMMA RB>); break;
-    }
-}
-template <int RA, int RB>
-__device__ __forceinline__ void run_pair2x(const DevOp &d, const amp *m, amp (&v)[NV], uint64_t g,
-                                           const uint64_t (&rg)[TILE_R]) {
-    if (d.kind == QVNT_RXX) QV_RUN(Pair2XBody<QVNT_RXX COMMA RA COMMA RB>);
-    else QV_RUN(Pair2XBody<QVNT_RYY COMMA RA COMMA RB>);
-}
-template <int RA, int RB>
-__device__ __forceinline__ void run_odd2(const DevOp &d, const amp *m, amp (&v)[NV], uint64_t g,
-                                         const uint64_t (&rg)[TILE_R]) {
-    switch (d.kind) {
-    case QVNT_SWAP: QV_RUN(Odd2Body<QVNT_SWAP COMMA RA COMMA RB>); break;
-    case QVNT_ISWAP: QV_RUN(Odd2Body<QVNT_ISWAP COMMA RA COMMA RB>); break;
-    case QVNT_SQRT_SWAP: QV_RUN(Odd2Body<QVNT_SQRT_SWAP COMMA RA COMMA RB>); break;
-    default: QV_RUN(Odd2Body<QVNT_SQRT_ISWAP COMMA RA COMMA RB>); break;
-    }
-}
-template <int RA, int RB>
-__device__ __forceinline__ void run_quad(const DevOp &d, const amp *m, amp (&v)[NV], uint64_t g,
-                                         const uint64_t (&rg)[TILE_R]) {
-    if (d.kind == QVNT_H2) QV_RUN(QuadBody<QVNT_H2 COMMA RA COMMA RB>);
-    else QV_RUN(QuadBody<QVNT_U2 COMMA RA COMMA RB>);
-}
-
-__device__ __forceinline__ void apply_op(const TOp *__restrict__ top, const amp *__restrict__ mats, amp (&v)[NV],
-                                      uint64_t g, const uint64_t (&rg)[TILE_R]) {
-    DevOp d = top->d;
-    const uint32_t form = top->form;
-    const int ra = top->ra, rb = top->rb;
-    const amp *m = mats + d.mat;
-    switch (form) {
-    case TF_DIAG:
-        switch (d.kind) {
-        case QVNT_Z: QV_RUN_D(DiagBody<QVNT_Z>); break;
-        case QVNT_S: QV_RUN_D(DiagBody<QVNT_S>); break;
-        case QVNT_T: QV_RUN_D(DiagBody<QVNT_T>); break;
-        case QVNT_RZ: QV_RUN_D(DiagBody<QVNT_RZ>); break;
-        default: QV_RUN_D(DiagBody<QVNT_RZZ>); break;
+template <int KIND, int RB, bool ALL>
+__device__ __forceinline__ void body_p1(amp (&v)[NV], const GP &g, const uint32_t ok) {
+    constexpr int HB = (RB == TR - 1) ? (1 << (TR - 2)) : (1 << (TR - 1));   // a slot bit other than RB
+    QV_FOR_K {
+        if ((K & (1 << RB)) || (K & HB)) continue;
+        if (ALL || ((ok >> K) & 1u)) {
+            QV_GUARD(ALL);
+            pair_update_s<KIND>(g, v[K], v[K | (1 << RB)], 0u, 1u);
         }
-        break;
-    case TF_PAIR1:
-        if (ra == 0) run_pair1<0>(d, m, v, g, rg);
-        else if (ra == 1) run_pair1<1>(d, m, v, g, rg);
-        else run_pair1<2>(d, m, v, g, rg);
-        break;
-    case TF_PAIR2X: {
-        const int lo = ra < rb ? ra : rb, hi = ra < rb ? rb : ra;
-        if (lo == 0 && hi == 1) run_pair2x<0, 1>(d, m, v, g, rg);
-        else if (lo == 0) run_pair2x<0, 2>(d, m, v, g, rg);
-        else run_pair2x<1, 2>(d, m, v, g, rg);
-        break;
     }
-    case TF_ODD2: {
-        const int lo = ra < rb ? ra : rb, hi = ra < rb ? rb : ra;
-        if (lo == 0 && hi == 1) run_odd2<0, 1>(d, m, v, g, rg);
-        else if (lo == 0) run_odd2<0, 2>(d, m, v, g, rg);
-        else run_odd2<1, 2>(d, m, v, g, rg);
-        break;
-    }
-    default:  // TF_QUAD
-        switch (ra * 3 + rb) {
-        case 1: run_quad<0, 1>(d, m, v, g, rg); break;
-        case 2: run_quad<0, 2>(d, m, v, g, rg); break;
-        case 3: run_quad<1, 0>(d, m, v, g, rg); break;
-        case 5: run_quad<1, 2>(d, m, v, g, rg); break;
-        case 6: run_quad<2, 0>(d, m, v, g, rg); break;
-        default: run_quad<2, 1>(d, m, v, g, rg); break;
+    if (QV_HALF_SPLIT) {
+        QV_FOR_K {
+            if ((K & (1 << RB)) || !(K & HB)) continue;
+            if (ALL || ((ok >> K) & 1u)) {
+                QV_GUARD(ALL);
+                pair_update_s<KIND>(g, v[K], v[K | (1 << RB)], 0u, 1u);
+            }
         }
-        break;
     }
 }
 
-__global__ void __launch_bounds__(TILE_THREADS, 3)
+// rxx/ryy on slot pair P: partner differs in both slots; the two members share their parity
+template <int KIND, int P, bool ALL>
+__device__ __forceinline__ void body_p2x(amp (&v)[NV], const GP &g, const uint32_t ok) {
+    constexpr int A = 1 << (2 * P), B = 2 << (2 * P);
+    QV_FOR_K {
+        if (K & A) continue;
+        if (ALL || ((ok >> K) & 1u)) {
+            QV_GUARD(ALL);
+            const unsigned sel = (K & B) ? 1u : 0u;      // parity of (i & ab): a clear, b = K's bit
+            pair_update_s<KIND>(g, v[K], v[K ^ (A | B)], sel, sel);
+        }
+    }
+}
+
+// swap family on slot pair P: only the odd-parity pair {a set, b set} changes
+template <int KIND, int P, bool ALL>
+__device__ __forceinline__ void body_odd(amp (&v)[NV], const GP &g, const uint32_t ok) {
+    constexpr int A = 1 << (2 * P), B = 2 << (2 * P);
+    QV_FOR_K {
+        if (K & (A | B)) continue;
+        if (ALL || ((ok >> K) & 1u)) {
+            QV_GUARD(ALL);
+            pair_update_s<KIND>(g, v[K | A], v[K | B], 1u, 1u);
+        }
+    }
+}
+
+// h2/u2: a = slot SA, b = slot SB
+template <int KIND, int SA, int SB, bool ALL>
+__device__ __forceinline__ void body_quad(amp (&v)[NV], const GP &g, const uint32_t ok) {
+    constexpr int A = 1 << SA, B = 1 << SB;
+    QV_FOR_K {
+        if (K & (A | B)) continue;
+        if (ALL || ((ok >> K) & 1u)) {
+            QV_GUARD(ALL);
+            amp q[4] = {v[K], v[K | A], v[K | B], v[K | A | B]};
+            quad_update<KIND>(g.mat, q);
+            v[K] = q[0];
+            v[K | A] = q[1];
+            v[K | B] = q[2];
+            v[K | A | B] = q[3];
+        }
+    }
+}
+
+// diagonal ops; cnt_t = popcount of the target mask over the thread + tile part of the index
+template <int KIND, bool PER_SLOT, bool ALL>
+__device__ __forceinline__ void body_diag(amp (&v)[NV], const GP &g, const uint32_t ok, const uint32_t cnt_t,
+                                          const uint32_t a_reg) {
+    if (!PER_SLOT) {
+        if (KIND == QVNT_Z && (cnt_t & 1u) == 0) return;
+        QV_FOR_K {
+            if (K >= NV / 2) continue;
+            if (ALL || ((ok >> K) & 1u)) {
+                QV_GUARD(ALL);
+                v[K] = diag_out_s<KIND>(g, v[K], cnt_t);
+            }
+        }
+        if (QV_HALF_SPLIT) {
+            QV_FOR_K {
+                if (K < NV / 2) continue;
+                if (ALL || ((ok >> K) & 1u)) {
+                    QV_GUARD(ALL);
+                    v[K] = diag_out_s<KIND>(g, v[K], cnt_t);
+                }
+            }
+        }
+    } else {
+        uint32_t b[TR];
+#pragma unroll
+        for (int j = 0; j < TR; ++j) b[j] = (a_reg >> j) & 1u;
+        QV_FOR_K {
+            if (ALL || ((ok >> K) & 1u)) {
+                QV_GUARD(ALL);
+                uint32_t cnt = cnt_t;
+#pragma unroll
+                for (int j = 0; j < TR; ++j)
+                    if (K & (1 << j)) cnt += b[j];
+                v[K] = diag_out_s<KIND>(g, v[K], cnt);
+            }
+        }
+    }
+}
+
+#define QV_P1(KIND, base)                                                   \
+    case base + 0: body_p1<KIND, 0, ALL>(v, g, ok); break;                  \
+    case base + 1: body_p1<KIND, 1, ALL>(v, g, ok); break;                  \
+    case base + 2: body_p1<KIND, 2, ALL>(v, g, ok); break;                  \
+    case base + 3: body_p1<KIND, 3, ALL>(v, g, ok); break;
+#define QV_P2X(KIND, base)                                                  \
+    case base + 0: body_p2x<KIND, 0, ALL>(v, g, ok); break;                 \
+    case base + 1: body_p2x<KIND, 1, ALL>(v, g, ok); break;
+#define QV_ODD(KIND, base)                                                  \
+    case base + 0: body_odd<KIND, 0, ALL>(v, g, ok); break;                 \
+    case base + 1: body_odd<KIND, 1, ALL>(v, g, ok); break;
+#define QV_DIAG(KIND, k5)                                                                              \
+    case MC_DU + k5: body_diag<KIND, false, ALL>(v, g, ok, __popc(grp & m.a_thr) + (fl & 7u), 0); break; \
+    case MC_DG + k5: body_diag<KIND, true, ALL>(v, g, ok, __popc(grp & m.a_thr) + (fl & 7u), m.a_reg & 0xFFFFu); break;
+
+// ALL: no control sits in a register slot (okmask = 0xFFFF) -- the common case runs without
+// any per-slot predicate.
+// One decoded op: the 32-byte MOp as it sits in shared memory (two 16-byte loads).
+struct MDec {
+    uint32_t w0;        // code | dagger << 8 | okmask << 16
+    uint32_t ctrl_thr;
+    uint32_t a_thr;
+    uint32_t a_reg;     // low 16 bits
+    double ph_re, ph_im;
+};
+
+// FULL: the interpreter carries the arms of every kind.  Passes made only of the common kinds
+// (diagonal class, x, y, rx, ry, h1) run the lean instance instead: the rare arms (u1/u2 keep a
+// whole matrix live, the two-bit ops have the most temporaries) set the register pressure of the
+// whole op loop, and without them its loop state stays in registers.
+template <bool ALL, bool FULL>
+__device__ __forceinline__ void apply_mop(const MDec &m, const uint32_t fl, const uint32_t grp,
+                                          const amp *__restrict__ mats, amp (&v)[NV]) {
+    GP g;
+    g.c = m.ph_re;
+    g.s = m.ph_im;
+    g.dagger = (m.w0 >> 8) & 0xFFu;
+    g.ybase = ~2u;                      // y on ONE bit (the planner splits multi-bit x/y masks)
+    g.mat = mats + m.a_thr;             // u1/u2 only
+    const uint32_t ok = m.w0 >> 16;
+    uint32_t code = m.w0 & 0xFFu;
+    asm volatile("" : "+r"(code));      // keep the dispatch value 32-bit: ptxas then builds a jump table (BRX)
+    switch (code) {
+    QV_DIAG(QVNT_Z, 0)
+    QV_DIAG(QVNT_S, 1)
+    QV_DIAG(QVNT_T, 2)
+    QV_DIAG(QVNT_RZ, 3)
+    QV_DIAG(QVNT_RZZ, 4)
+    QV_P1(QVNT_X, MC_P1 + 0)
+    QV_P1(QVNT_Y, MC_P1 + 4)
+    QV_P1(QVNT_RX, MC_P1 + 8)
+    QV_P1(QVNT_RY, MC_P1 + 12)
+    QV_P1(QVNT_H1, MC_P1 + 16)
+    default: break;
+    }
+    if (!FULL) return;
+    switch (code) {
+    QV_P1(QVNT_U1, MC_P1 + 20)
+    QV_P2X(QVNT_RXX, MC_P2X + 0)
+    QV_P2X(QVNT_RYY, MC_P2X + 2)
+    QV_ODD(QVNT_SWAP, MC_ODD + 0)
+    QV_ODD(QVNT_ISWAP, MC_ODD + 2)
+    QV_ODD(QVNT_SQRT_SWAP, MC_ODD + 4)
+    QV_ODD(QVNT_SQRT_ISWAP, MC_ODD + 6)
+    case MC_H2 + 0: body_quad<QVNT_H2, 0, 1, ALL>(v, g, ok); break;
+    case MC_H2 + 1: body_quad<QVNT_H2, 2, 3, ALL>(v, g, ok); break;
+    case MC_U2 + 0: body_quad<QVNT_U2, 0, 1, ALL>(v, g, ok); break;
+    case MC_U2 + 1: body_quad<QVNT_U2, 1, 0, ALL>(v, g, ok); break;
+    case MC_U2 + 2: body_quad<QVNT_U2, 2, 3, ALL>(v, g, ok); break;
+    case MC_U2 + 3: body_quad<QVNT_U2, 3, 2, ALL>(v, g, ok); break;
+    default: break;
+    }
+}
+
+// One stage on one tile: every thread takes the 16 amplitudes of its group(s) into registers,
+// runs the stage's ops on them and writes them back.  All addresses are 32-bit shared-window
+// offsets; the op range [ob, oe) is relative to the pass's first op.
+template <bool FULL>
+__device__ __forceinline__ void run_stage(const uint32_t tile_s, const uint32_t stage_s, const uint32_t ops_s,
+                                          const uint32_t flags_s, const uint32_t ob, const uint32_t oe,
+                                          const uint32_t n_t, const amp *__restrict__ mats) {
+    uint32_t sw[8];      // the TStage: op_begin, op_end, r_lpos[4], t_lpos[16], pad
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(sw[0]), "=r"(sw[1]), "=r"(sw[2]), "=r"(sw[3]) : "r"(stage_s) : "memory");
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(sw[4]), "=r"(sw[5]), "=r"(sw[6]), "=r"(sw[7]) : "r"(stage_s + 16u) : "memory");
+    uint32_t c[TR];
+#pragma unroll
+    for (int j = 0; j < TR; ++j) c[j] = 16u * swz(1u << ((sw[2] >> (8 * j)) & 0xFFu));
+    const uint32_t groups = 1u << n_t;
+    for (uint32_t grp = threadIdx.x; grp < groups; grp += blockDim.x) {
+        uint32_t jl = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 16; ++k) {
+            if (k < n_t) jl |= ((grp >> k) & 1u) << ((sw[3 + (k >> 2)] >> (8 * (k & 3))) & 0xFFu);
+        }
+        const uint32_t mine_o = 16u * swz(jl);      // byte offset of slot pattern 0 in the tile
+        // (the XOR applies to the offset inside the tile: the tile itself is only 16-byte aligned)
+        amp v[NV];
+#pragma unroll
+        for (int K = 0; K < NV; ++K) {
+            uint32_t a = mine_o;
+            if (K & 1) a ^= c[0];
+            if (K & 2) a ^= c[1];
+            if (K & 4) a ^= c[2];
+            if (K & 8) a ^= c[3];
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n"
+                         : "=d"(v[K].x), "=d"(v[K].y)
+                         : "r"(tile_s + a)
+                         : "memory");
+        }
+        // ob / oe come from the kernel parameters (uniform registers): the loop control costs no
+        // vector registers, which the arms below need for their 16 amplitudes + products.
+        // The descriptor of op o+1 is fetched before op o's arithmetic is issued, so its
+        // shared-memory latency hides under the FP64 burst of op o.
+        MDec m_nx;
+        uint32_t fl_nx;
+        auto fetch = [&](uint32_t o) {
+            const uint32_t op_a = ops_s + 32u * o, fl_a = flags_s + o;
+            asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(fl_nx) : "r"(fl_a) : "memory");
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+                         : "=r"(m_nx.w0), "=r"(m_nx.ctrl_thr), "=r"(m_nx.a_thr), "=r"(m_nx.a_reg)
+                         : "r"(op_a)
+                         : "memory");
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n"
+                         : "=d"(m_nx.ph_re), "=d"(m_nx.ph_im)
+                         : "r"(op_a + 16u)
+                         : "memory");
+        };
+        if (ob < oe) fetch(ob);
+        for (uint32_t o = ob; o < oe; ++o) {
+            const MDec m = m_nx;
+            const uint32_t fl = fl_nx;
+#if QV_OP_PREFETCH
+            if (o + 1 < oe) fetch(o + 1);
+#endif
+            if (!(fl & 0x80u) || (~grp & m.ctrl_thr)) {
+#if !QV_OP_PREFETCH
+                if (o + 1 < oe) fetch(o + 1);
+#endif
+                continue;
+            }
+            if ((m.w0 >> 16) == 0xFFFFu) apply_mop<true, FULL>(m, fl, grp, mats, v);
+            else apply_mop<false, FULL>(m, fl, grp, mats, v);
+#if !QV_OP_PREFETCH
+            if (o + 1 < oe) fetch(o + 1);
+#endif
+        }
+        // recompute the 16 slot addresses instead of keeping them live across the op loop
+        uint32_t mine_o2 = mine_o;
+        asm volatile("" : "+r"(mine_o2));
+#pragma unroll
+        for (int K = 0; K < NV; ++K) {
+            uint32_t a = mine_o2;
+            if (K & 1) a ^= c[0];
+            if (K & 2) a ^= c[1];
+            if (K & 4) a ^= c[2];
+            if (K & 8) a ^= c[3];
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(tile_s + a), "d"(v[K].x), "d"(v[K].y)
+                         : "memory");
+        }
+    }
+}
+
+// Kernel configurations: <threads per CTA, min CTAs per SM, tile buffers>.
+//   T <= 11: 128 threads, 3 CTAs/SM, TWO tile buffers -- the next tile's cp.async loads are in
+//            flight while the current tile is computed, stores are fire-and-forget, so the HBM
+//            phases overlap the FP64 phases inside each CTA.
+//   T == 12: 256 threads, 2 CTAs/SM, one 64 KiB buffer (two do not fit twice per SM).
+template <int THREADS, int MINB, int NB, bool FULL>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr hdr,
-            const TStage *__restrict__ stages, const TOp *__restrict__ ops, const amp *__restrict__ mats) {
+            const TStage *__restrict__ g_stages, const MOp *__restrict__ g_ops,
+            const MBase *__restrict__ g_bases, const amp *__restrict__ mats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    amp *tile = reinterpret_cast<amp *>(smem_raw);
-    __shared__ uint64_t s_hoff[1 << TILE_MAX_HIGH];   // gathered-bit pattern -> global index bits
-    __shared__ amp *s_seg[MAX_WORLD];
-    __shared__ uint8_t s_gpos[16];
-    __shared__ uint8_t s_fxpos[64];
-
-    const uint32_t tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     const uint32_t T = hdr.T, L = hdr.L;
+    const uint32_t n_ops = hdr.n_ops, n_stages = hdr.n_stages;
     const uint32_t tile_len = 1u << T;
+    const uint32_t tile_bytes = 16u << T;
     const uint32_t lmask = (1u << L) - 1u;
-    const uint32_t n_fx = hdr.fx.n;
-    if (tid < 16) s_gpos[tid] = hdr.gpos[tid];
-    if (tid < 64) s_fxpos[tid] = hdr.fx.pos[tid];
-    if (tid < MAX_WORLD) s_seg[tid] = segs.seg[tid];
-    __syncthreads();
-    for (uint32_t h = tid; h < (1u << (T - L)); h += TILE_THREADS) {
-        uint64_t gb = 0;
-        for (uint32_t j = 0; j < T - L; ++j)
-            if ((h >> j) & 1u) gb |= 1ull << s_gpos[L + j];
-        s_hoff[h] = gb;
+    const uint32_t n_chunks = 1u << (T - L);
+    const uint32_t flags_stride = (n_ops + 15u) & ~15u;
+
+    // shared memory carve-up (16-byte aligned sections first)
+    unsigned char *tiles_b = smem_raw;                                            // NB * (16 << T)
+    MOp *s_ops = reinterpret_cast<MOp *>(smem_raw + (size_t)NB * tile_bytes);      // 32 * n_ops
+    TStage *s_stages = reinterpret_cast<TStage *>(s_ops + n_ops);                  // 32 * n_stages
+    amp **s_cptr_all = reinterpret_cast<amp **>(s_stages + n_stages);              // NB * 8 * n_chunks
+    uint8_t *s_flags_all = reinterpret_cast<uint8_t *>(s_cptr_all + NB * n_chunks);  // NB * flags_stride
+
+    // the pass program: same for every tile this CTA processes
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g_ops + hdr.op_begin);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_ops);
+        for (uint32_t i = tid; i < 2 * n_ops; i += nthr) dst[i] = src[i];
+        src = reinterpret_cast<const uint4 *>(g_stages + hdr.stage_begin);
+        dst = reinterpret_cast<uint4 *>(s_stages);
+        for (uint32_t i = tid; i < 2 * n_stages; i += nthr) dst[i] = src[i];
     }
-    __syncthreads();
     const uint32_t shard_shift = segs.shift;
     const uint64_t shard_mask = (1ull << shard_shift) - 1ull;
-    const uint32_t n_t = T - TILE_R;                 // thread bits per stage
-    const uint32_t groups = 1u << n_t;
+    const uint32_t n_t = T - TR;                     // thread bits per stage
+    const MBase *bases = g_bases + hdr.op_begin;
+    const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(tiles_b);
+    const uint32_t ops_s = (uint32_t)__cvta_generic_to_shared(s_ops);
+    const uint32_t stages_s = (uint32_t)__cvta_generic_to_shared(s_stages);
+    const uint32_t flags_all_s = (uint32_t)__cvta_generic_to_shared(s_flags_all);
+    __syncthreads();
 
-    for (uint64_t tile_i = blockIdx.x; tile_i < hdr.n_tiles; tile_i += gridDim.x) {
-        // tile counter -> base index (tile bits clear)
-        uint64_t base = tile_i;
-        for (uint32_t k = 0; k < n_fx; ++k) {
-            const uint32_t p = s_fxpos[k];
-            base = ((base >> p) << (p + 1)) | (base & ((1ull << p) - 1ull));
+    // Metadata of the first tile >= t (stepping by the grid) that some op of this pass can change:
+    // per-op flags (bit 7: controls outside the tile satisfied; bits 0-2: popcount of the diagonal
+    // target mask over the bits outside the tile, mod 8) and the chunk pointers.  Tiles no op
+    // touches (multi-controlled gates) are skipped without being read.  Returns n_tiles if none.
+    auto prepare = [&](uint64_t t, uint32_t slot) -> uint64_t {
+        uint8_t *flags = s_flags_all + slot * flags_stride;
+        amp **cptr = s_cptr_all + slot * n_chunks;
+        for (; t < hdr.n_tiles; t += gridDim.x) {
+            uint64_t base = t;               // tile counter -> global base index (tile bits clear)
+            for (uint32_t k = 0; k < hdr.n_runs; ++k) {
+                const uint32_t p = hdr.run_pos[k], len = hdr.run_len[k];
+                base = ((base >> p) << (p + len)) | (base & ((1ull << p) - 1ull));
+            }
+            base |= hdr.fx_val | hdr.base_or;
+            int any = 0;
+            for (uint32_t o = tid; o < n_ops; o += nthr) {
+                const MBase b = bases[o];
+                const uint32_t okb = ((~base & b.ctrl_base) == 0) ? 0x80u : 0u;
+                flags[o] = (uint8_t)(okb | ((uint32_t)__popcll(base & b.a_base) & 7u));
+                any |= (int)okb;
+            }
+            for (uint32_t c = tid; c < n_chunks; c += nthr) {
+                uint64_t gidx = base;
+                for (uint32_t j = 0; j < T - L; ++j)
+                    if ((c >> j) & 1u) gidx |= 1ull << hdr.gpos[L + j];
+                cptr[c] = segs.seg[gidx >> shard_shift] + (gidx & shard_mask);
+            }
+            if (__syncthreads_or(any)) return t;
         }
-        base |= hdr.fx.val | hdr.base_or;
+        return hdr.n_tiles;
+    };
+    // 2^(T-L) chunks of 2^L contiguous amplitudes, 16-byte cp.async, swizzled; one commit group
+    auto issue_load = [&](uint32_t slot) {
+        amp *const *cptr = s_cptr_all + slot * n_chunks;
+        unsigned char *tb = tiles_b + slot * tile_bytes;
+        for (uint32_t j = tid; j < tile_len; j += nthr) cp_async_16(tb + 16u * swz(j), cptr[j >> L] + (j & lmask));
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
 
-        // ---- load: 2^(T-L) chunks of 2^L contiguous amplitudes, 16-byte cp.async, swizzled ----
-        for (uint32_t j = tid; j < tile_len; j += TILE_THREADS) {
-            const uint64_t gidx = base | s_hoff[j >> L] | (uint64_t)(j & lmask);
-            const amp *src = s_seg[gidx >> shard_shift] + (gidx & shard_mask);
-            cp_async_16(&tile[swz(j)], src);
+    uint32_t slot = 0;
+    uint64_t t_cur = prepare(blockIdx.x, slot);
+    if (t_cur < hdr.n_tiles) issue_load(slot);
+    while (t_cur < hdr.n_tiles) {
+        uint64_t t_next = hdr.n_tiles;
+        if (NB == 2) {
+            t_next = prepare(t_cur + gridDim.x, slot ^ 1u);
+            if (t_next < hdr.n_tiles) {
+                issue_load(slot ^ 1u);
+                asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            }
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         }
-        cp_async_wait_all();
         __syncthreads();
+        const uint32_t tile_s = tiles_s + slot * tile_bytes;
+        const uint32_t flags_s = flags_all_s + slot * flags_stride;
 
-        // ---- stages: 2^TILE_R amplitudes per thread in registers ---------------------------
-        for (uint32_t s = 0; s < hdr.n_stages; ++s) {
-            const TStage *st = stages + hdr.stage_begin + s;
-            uint32_t rl[TILE_R];
-            uint64_t rg[TILE_R];
-#pragma unroll
-            for (int j = 0; j < TILE_R; ++j) {
-                const uint32_t lp = st->r_lpos[j];
-                rl[j] = 1u << lp;
-                rg[j] = 1ull << s_gpos[lp];
-            }
-            const uint32_t ob = st->op_begin, oe = st->op_end;
-            for (uint32_t grp = tid; grp < groups; grp += TILE_THREADS) {
-                uint32_t jl = 0;
-                uint64_t g = base;
-                for (uint32_t k = 0; k < n_t; ++k) {
-                    if ((grp >> k) & 1u) {
-                        const uint32_t lp = st->t_lpos[k];
-                        jl |= 1u << lp;
-                        g |= 1ull << s_gpos[lp];
-                    }
-                }
-                amp v[NV];
-#pragma unroll
-                for (int k = 0; k < NV; ++k) {
-                    const uint32_t j = jl | ((k & 1) ? rl[0] : 0u) | ((k & 2) ? rl[1] : 0u) | ((k & 4) ? rl[2] : 0u);
-                    v[k] = tile[swz(j)];
-                }
-                for (uint32_t o = ob; o < oe; ++o) apply_op(ops + o, mats, v, g, rg);
-#pragma unroll
-                for (int k = 0; k < NV; ++k) {
-                    const uint32_t j = jl | ((k & 1) ? rl[0] : 0u) | ((k & 2) ? rl[1] : 0u) | ((k & 4) ? rl[2] : 0u);
-                    tile[swz(j)] = v[k];
-                }
-            }
+        // ---- stages: 16 amplitudes per thread in registers ------------------------------------
+        for (uint32_t s = 0; s < n_stages; ++s) {
+            run_stage<FULL>(tile_s, stages_s + 32u * s, ops_s, flags_s, s ? hdr.stage_end[s - 1] : 0u, hdr.stage_end[s],
+                      n_t, mats);
             __syncthreads();
         }
 
-        // ---- store back in place ----------------------------------------------------------
-        for (uint32_t j = tid; j < tile_len; j += TILE_THREADS) {
-            const uint64_t gidx = base | s_hoff[j >> L] | (uint64_t)(j & lmask);
-            amp *dst = s_seg[gidx >> shard_shift] + (gidx & shard_mask);
-            *dst = tile[swz(j)];
+        // ---- store back in place (fire and forget) --------------------------------------------
+        {
+            amp *const *cptr = s_cptr_all + slot * n_chunks;
+            const unsigned char *tb = tiles_b + slot * tile_bytes;
+            for (uint32_t j = tid; j < tile_len; j += nthr)
+                *(cptr[j >> L] + (j & lmask)) = *reinterpret_cast<const amp *>(tb + 16u * swz(j));
         }
-        __syncthreads();
+        __syncthreads();                 // this slot's tile buffer and metadata are free again
+        if (NB == 1) {
+            t_next = prepare(t_cur + gridDim.x, slot);
+            if (t_next < hdr.n_tiles) issue_load(slot);
+        } else {
+            slot ^= 1u;
+        }
+        t_cur = t_next;
     }
 }
 
-int tile_kernel_setup() {
-    static bool done = false;
-    static cudaError_t err = cudaSuccess;
-    // per-device attribute; cheap enough to set on every device we see
-    err = cudaFuncSetAttribute(k_tile_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)(sizeof(amp) << TILE_MAX_BITS));
-    done = true;
-    (void)done;
-    return err == cudaSuccess ? 0 : -1;
+constexpr size_t TILE_SMEM_MAX = 227u * 1024u;
+
+static size_t tile_smem_bytes(const TPassHdr &h, int nb) {
+    return (size_t)nb * ((size_t)16 << h.T) + (size_t)32 * h.n_ops + (size_t)32 * h.n_stages +
+           (size_t)nb * ((size_t)8 << (h.T - h.L)) + (size_t)nb * ((h.n_ops + 15u) & ~15u);
 }
 
+typedef void (*tile_kernel_t)(const Segs, const TPassHdr, const TStage *, const MOp *, const MBase *, const amp *);
+
+template <int THREADS, int MINB, int NB>
+static tile_kernel_t pick_kernel(bool full) {
+    return full ? k_tile_pass<THREADS, MINB, NB, true> : k_tile_pass<THREADS, MINB, NB, false>;
+}
+
+int tile_kernel_setup() {
+    bool ok = true;
+    for (int full = 0; full < 2; ++full) {
+        const tile_kernel_t ks[3] = {pick_kernel<128, 3, 2>(full), pick_kernel<128, 3, 1>(full),
+                                     pick_kernel<256, 2, 1>(full)};
+        for (tile_kernel_t k : ks)
+            ok = ok && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)TILE_SMEM_MAX) == cudaSuccess;
+    }
+    return ok ? 0 : -1;
+}
+
+int g_tile_nbuf = 0;     // tuning knob (option "tile_nbuf"): 0 = auto, 1 / 2 = force for T <= 11
+
 int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, const TStage *d_stages,
-                     const TOp *d_ops, const amp *mat_table, int sm_count) {
+                     const MOp *d_ops, const MBase *d_bases, const amp *mat_table, int sm_count) {
     if (hdr.T < TILE_MIN_BITS || hdr.T > TILE_MAX_BITS || hdr.L > hdr.T || hdr.T - hdr.L > TILE_MAX_HIGH ||
-        hdr.n_tiles == 0)
+        hdr.n_tiles == 0 || hdr.n_ops == 0 || hdr.n_ops > (uint32_t)TILE_MAX_OPS ||
+        hdr.n_stages > (uint32_t)TILE_MAX_STAGES)
         return -1;
-    const size_t smem = sizeof(amp) << hdr.T;
-    int per_sm = (int)((200u * 1024u) / (smem + 2048));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;
+    tile_kernel_t kern;
+    int threads, nb;
+    if (hdr.T >= 12) {
+        kern = pick_kernel<256, 2, 1>(hdr.full != 0);
+        threads = 256;
+        nb = 1;
+    } else {
+        threads = 1 << (hdr.T - TILE_R);
+        if (threads < 32) threads = 32;
+        if (threads > 128) threads = 128;
+        nb = 2;
+        kern = pick_kernel<128, 3, 2>(hdr.full != 0);
+        if (g_tile_nbuf == 1 || tile_smem_bytes(hdr, 2) > TILE_SMEM_MAX) {   // (very long pass programs)
+            nb = 1;
+            kern = pick_kernel<128, 3, 1>(hdr.full != 0);
+        }
+    }
+    const size_t smem = tile_smem_bytes(hdr, nb);
+    if (smem > TILE_SMEM_MAX) return -1;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
     uint64_t grid = (uint64_t)sm_count * per_sm;
     if (grid > hdr.n_tiles) grid = hdr.n_tiles;
-    k_tile_pass<<<(unsigned)grid, TILE_THREADS, smem, st>>>(segs, hdr, d_stages, d_ops, mat_table);
+    kern<<<(unsigned)grid, threads, smem, st>>>(segs, hdr, d_stages, d_ops, d_bases, mat_table);
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 
