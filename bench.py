@@ -222,6 +222,8 @@ def run_ours(args):
         reg.set_option("fuse", 0)
     if args.nbuf:
         reg.set_option("tile_nbuf", args.nbuf)
+    if args.stagger >= 0:
+        reg.set_option("tile_stagger", args.stagger)
 
     def barrier():
         if dist is not None:
@@ -313,7 +315,7 @@ def run_ours(args):
         "config": {"workload": name, "qubits": n, "single_ops": n_ops, "state_bytes": 16 << n,
                    "l2": "state (>= 4 GiB) is far larger than the 126 MB L2; no flush needed",
                    "sharding": f"top {world.bit_length() - 1} qubits across {world} GPU(s)",
-                   "fuse": not args.no_fuse, "tile_bits": args.tile_bits or 12, "chunk_bits": args.chunk_bits or 7},
+                   "fuse": not args.no_fuse, "tile_bits": args.tile_bits or 11, "chunk_bits": args.chunk_bits or 4},
         "amplitude_gbs": value * 32 * (1 << n) / 1e9,
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
     }
@@ -343,6 +345,7 @@ def main():
     ap.add_argument("--tile-bits", type=int, default=0)
     ap.add_argument("--nbuf", type=int, default=0, help="tile buffers per CTA for T <= 11 (0 = auto)")
     ap.add_argument("--chunk-bits", type=int, default=0)
+    ap.add_argument("--stagger", type=int, default=-1, help="start offset (cycles) between the CTAs of an SM")
     ap.add_argument("--no-fuse", action="store_true", help="one in-place sweep per SingleOp")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -176,6 +176,18 @@ static int create_common(uint32_t q_num, uint64_t state, uint32_t rank, uint32_t
         cudaEventCreateWithFlags(&r->stage_free, cudaEventDisableTiming) != cudaSuccess)
         return fail(cuda_fail(cudaGetLastError(), "scratch allocation"));
     QV_CUDA(cudaMemsetAsync(r->mailbox, 0, 4096, r->stream));
+    {
+        // Everything the hot path and measure_mask need is allocated up front: allocation calls
+        // synchronise the whole device, which must not happen while a peer shard's barrier kernel
+        // is waiting for this shard (and costs milliseconds on the hot path).
+        const uint64_t n1 = (r->local_len + SAMPLE_BLOCK - 1) / SAMPLE_BLOCK;
+        const uint64_t n2b = (n1 + SAMPLE_BLOCK - 1) / SAMPLE_BLOCK;
+        if ((rc = ensure_dev((void **)&r->d_l1, &r->l1_cap, n1 * sizeof(double))) ||
+            (rc = ensure_dev((void **)&r->d_l2, &r->l2_cap, n2b * sizeof(double))) ||
+            (rc = ensure_stage(r, (size_t)2 << 20)) || (rc = ensure_dev(&r->d_ops, &r->d_ops_cap, (size_t)2 << 20)) ||
+            (rc = ensure_dev((void **)&r->d_mat, &r->d_mat_cap, (size_t)1 << 16)))
+            return fail(rc);
+    }
     for (int i = 0; i < MAX_WORLD; ++i) r->segs.seg[i] = nullptr;
     r->segs.seg[rank] = r->psi;
     r->segs.shift = r->n_local;
@@ -605,6 +617,7 @@ int qvnt_reg_set_option(qvnt_reg_t *r, const char *key, int64_t value) {
         r->opt_chunk_bits = (int)value;
     } else if (!strcmp(key, "tma")) r->opt_tma = value != 0;
     else if (!strcmp(key, "tile_nbuf")) g_tile_nbuf = (int)value;
+    else if (!strcmp(key, "tile_stagger")) g_tile_stagger = (int)value;
     else if (!strcmp(key, "profile")) {
         int rc = use(r);
         if (rc) return rc;

@@ -45,6 +45,11 @@ constexpr int TILE_R = 4;
 constexpr int TILE_NV = 1 << TILE_R;
 constexpr int TILE_MAX_BITS = 12;
 constexpr int TILE_MIN_BITS = 4;
+// Defaults measured on configs[1] (tools/exp.sh): 2^11-amplitude tiles (32 KiB) made of 2^4-amplitude
+// chunks (256 B) + 7 gathered bits, 4 CTAs of 128 threads per SM -> 8.0k gates/s; 2^12 tiles with
+// 2 CTAs of 256 threads reach 7.6k (fewer passes, but half the warps to hide latency with).
+constexpr int TILE_DEFAULT_BITS = 11;
+constexpr int TILE_DEFAULT_CHUNK = 4;
 constexpr int TILE_MAX_HIGH = 8;   // gathered (non-contiguous) tile bits: T - L <= 8
 constexpr int TILE_THREADS = 256;  // = 2^(TILE_MAX_BITS - TILE_R)
 constexpr int TILE_MAX_OPS = 2048; // SingleOps per pass (their descriptors live in shared memory)
@@ -55,7 +60,8 @@ enum TForm : uint32_t {
     TF_PAIR1 = 1,   // x/y/rx/ry/h1/u1 on one bit: partner differs in slot ra
     TF_PAIR2X = 2,  // rxx/ryy: partner differs in slots ra and rb
     TF_ODD2 = 3,    // swap family: odd-parity pair {slot ra set, slot rb set}
-    TF_QUAD = 4     // h2/u2: a = slot ra, b = slot rb
+    TF_QUAD = 4,    // h2/u2: a = slot ra, b = slot rb
+    TF_LAZYX = 5    // x between threads: no register slot
 };
 
 // Dispatch codes of the stage interpreter (tile.cu).  Two-bit ops sit on the slot pairs
@@ -71,17 +77,43 @@ enum MCode : uint8_t {
     MC_COUNT = 52
 };
 
-struct __align__(16) MOp {   // 32 bytes, staged in shared memory
-    uint8_t code;        // MCode
-    uint8_t dagger;
+// Dispatch codes of the FAST stage interpreter (tile.cu): passes made only of the common kinds
+// (x, y, rx, ry, h1 on one bit; z/s/t on one bit; rz; rzz) are lowered by the planner to five
+// coefficient-driven forms, so one arm serves several kinds:
+//   FC_PR  real pair      new0 = c0*p0 + c1*p1 ; new1 = c2*p0 + c3*p1            (ry)
+//   FC_PX  crossed pair   new0 = c0*p0 - i*c1*p1 ; new1 = -i*c2*p0 + c3*p1        (rx, y)
+//   FC_SW  swap           new0 = p1 ; new1 = p0                                   (x)
+//   FC_DU / FC_DS / FC_DG diagonal: p *= (parity of i & target ? f1 : f0), f0 = (c0,c1), f1 = (c2,c3);
+//          DU: no target bit in a register slot; DS: exactly one (slot j); DG: any a_reg
+enum FCode : uint8_t {
+    FC_PR = 0,    // + slot
+    FC_PX = 4,    // + slot
+    FC_SW = 8,    // + slot
+    FC_DU = 12,
+    FC_DS = 13,   // + slot
+    FC_DG = 17,
+    FC_PA = 18,   // + slot: add/sub pair  new0 = (p0 + p1) * c0 ; new1 = (p0 - p1) * c0   (h1: the
+                  //         reference's own operation order, h1.rs:16-22; h2 halves use c0 = 1 and 0.5)
+    FC_LX = 22,   // lazy x: target and controls on thread / outer bits (a_thr = target's thread bit,
+                  //         a_reg = its tile-local position); no register slot involved
+    FC_COUNT = 23,
+    FC_ALL = 23   // added to the code when no control sits in a register slot (okmask == 0xFFFF)
+};
+constexpr uint8_t MOP_SKIP0 = 0x02;   // MOp::dagger bit 1 (fast diagonal forms): f0 == 1, even parity untouched
+
+struct __align__(16) MOp {   // 48 bytes, staged in shared memory
+    uint8_t code;        // MCode (full interpreter) or FCode (fast interpreter)
+    uint8_t dagger;      // bit 0: dagger; bit 1: MOP_SKIP0
     uint16_t okmask;     // bit K: register slot pattern K satisfies the controls held in register slots
     uint32_t ctrl_thr;   // controls on thread bits (bit k = thread bit k of the stage)
     uint32_t a_thr;      // diagonal class: target-mask bits on thread bits; u1/u2: matrix table index
     uint16_t a_reg;      // diagonal class: target-mask bits on register slots
     uint16_t _pad;
-    double ph_re, ph_im;
+    double ph_re, ph_im; // full: (cos t/2, sin t/2); fast: c0, c1
+    double c2, c3;       // fast only
 };
-static_assert(sizeof(MOp) == 32, "MOp layout");
+static_assert(sizeof(MOp) == 48, "MOp layout");
+constexpr uint32_t MOP_BYTES = 48;
 
 struct MBase {           // per-op masks over the index bits that are NOT tile bits (global numbering)
     uint64_t ctrl_base;
@@ -110,7 +142,8 @@ struct TPassHdr {
     uint64_t n_tiles;            // tiles this rank processes
     uint64_t base_or;            // this rank's bits for the global qubits that are NOT tile bits
     uint32_t touches_peer;       // some tile bit is a rank bit
-    uint32_t full;               // some op needs the full interpreter (u1/u2, two-bit pair ops, h2)
+    uint32_t full;               // some op needs the full interpreter (u1/u2, two-bit pair ops, multi-bit masks)
+    uint32_t waves, stagger_cycles;   // filled by launch_tile_pass: CTAs per SM, start offset between them
     uint16_t stage_end[TILE_MAX_STAGES];   // ops of stage s: [stage_end[s-1], stage_end[s]) relative to op_begin
     Fixed fx;                    // the same enumeration bit by bit (host side: describe / tests)
 };
@@ -119,6 +152,7 @@ int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, con
                      const MOp *d_ops, const MBase *d_bases, const amp *mat_table, int sm_count);
 int tile_kernel_setup();
 extern int g_tile_nbuf;
+extern int g_tile_stagger;
 
 // ---- measurement / utility kernels (measure.cu) -----------------------------
 constexpr int REDUCE_BLOCKS_MAX = 4096;

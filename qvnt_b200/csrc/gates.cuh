@@ -137,6 +137,7 @@ __device__ __forceinline__ PairMid pair_mid(const GP &g, amp p0, amp p1, unsigne
         if (sel) p0 = c_neg(p0);
         m.t[0] = p0.x + p1.x;
         m.t[1] = p0.y + p1.y;
+        m.t[2] = g.c;               // 1/sqrt(2) (planner.cu sets it; the halves of a split h2 carry 1 and 0.5)
     } else if (KIND == QVNT_U1) {                           // u1.rs:17-25
         // sel == 0: M[0]*p0 + M[1]*p1 ; sel == 1: M[2]*p1 + M[3]*p0   (p0 = self, p1 = partner)
         const amp A = sel == 0 ? g.mat[0] : g.mat[2], B = sel == 0 ? g.mat[1] : g.mat[3];
@@ -179,7 +180,7 @@ __device__ __forceinline__ amp pair_fin(const PairMid &m) {
     } else if (KIND == QVNT_RY) {
         return make_double2(m.t[0] + m.t[1], m.t[2] + m.t[3]);
     } else if (KIND == QVNT_H1) {
-        return make_double2(m.t[0] * QV_FRAC_1_SQRT_2, m.t[1] * QV_FRAC_1_SQRT_2);
+        return make_double2(m.t[0] * m.t[2], m.t[1] * m.t[2]);
     } else if (KIND == QVNT_U1) {
         return make_double2((m.t[0] - m.t[1]) + (m.t[4] - m.t[5]), (m.t[2] + m.t[3]) + (m.t[6] + m.t[7]));
     } else if (KIND == QVNT_SQRT_SWAP) {

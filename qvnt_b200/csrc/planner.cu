@@ -17,6 +17,7 @@
 // (|diff| ~ 1e-16, parity bar 1e-10); with option "fuse" = 0 every op is its own sweep
 // and the result is bit-identical to the reference arithmetic.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "reg.h"
@@ -78,6 +79,9 @@ static int lower_ops(const PlanCfg &r, const qvnt_op_t *ops, size_t n_ops, std::
                      std::vector<amp> &mats) {
     const uint64_t gmask = r.q_mask() & ~((1ull << r.n_local) - 1ull);
     const bool tile_possible = r.n_local >= (uint32_t)TILE_MIN_BITS;
+    // a lone SingleOp keeps the reference's exact arithmetic (one direct sweep); op LISTS are
+    // refactored for the fused pass (exact factorisations, FMA arithmetic: parity bar 1e-10)
+    const bool split_fused = r.fuse && tile_possible && n_ops > 1;
     pl.reserve(n_ops + 16);
     for (size_t k = 0; k < n_ops; ++k) {
         int rc = validate(r, ops[k], k);
@@ -97,6 +101,7 @@ static int lower_ops(const PlanCfg &r, const qvnt_op_t *ops, size_t n_ops, std::
         p.d.ctrl = o.ctrl;
         p.d.ph_re = o.phase_re;
         p.d.ph_im = o.phase_im;
+        if (o.kind == QVNT_H1) p.d.ph_re = QV_FRAC_1_SQRT_2;     // the butterfly's scale (h1.rs:21)
         if (o.kind == QVNT_U1 || o.kind == QVNT_U2) {
             const int cnt = o.kind == QVNT_U1 ? 4 : 16;
             p.d.mat = (uint32_t)mats.size();
@@ -114,6 +119,37 @@ static int lower_ops(const PlanCfg &r, const qvnt_op_t *ops, size_t n_ops, std::
                 q.dg = q.d.ctrl;
                 pl.push_back(q);
                 m &= m - 1;
+            }
+            continue;
+        }
+        if (split_fused && (o.kind == QVNT_Z || o.kind == QVNT_S || o.kind == QVNT_T) &&
+            pc64(o.a_mask) > 1) {
+            // z/s/t(m) = prod_b z/s/t(b): the phase of an amplitude is w^popcount(i & m)
+            // (z.rs:15-21, s.rs:19-25, t.rs:24-35), a product of one factor per set bit.
+            uint64_t m = o.a_mask;
+            while (m) {
+                POp q = p;
+                q.d.a = m & (~m + 1);
+                q.mix = 0;
+                q.dg = q.d.ctrl | q.d.a;
+                pl.push_back(q);
+                m &= m - 1;
+            }
+            continue;
+        }
+        if (split_fused && o.kind == QVNT_H2) {
+            // h2(a, b) = h1(a) h1(b) (h2.rs:22-38 is the product of the two butterflies)
+            for (int half = 0; half < 2; ++half) {
+                POp q = p;
+                q.d.kind = QVNT_H1;
+                q.cls = CLS_PAIR;
+                q.d.a = half ? o.b_mask : o.a_mask;
+                q.d.b = 0;
+                q.d.ph_re = half ? 0.5 : 1.0;      // h2.rs:37 scales the sum of four once, by 0.5
+                q.d.ph_im = 0.0;
+                q.mix = q.d.a;
+                q.dg = q.d.ctrl;
+                pl.push_back(q);
             }
             continue;
         }
@@ -190,6 +226,19 @@ static void greedy_select(const std::vector<POp> &pl, const std::vector<int> &ca
     set_out = set;
 }
 
+// Kinds the fast stage interpreter carries (tile.cu, FCode)
+static bool fast_kind(const POp &p) {
+    switch (p.d.kind) {
+    case QVNT_X: case QVNT_Y: case QVNT_RX: case QVNT_RY: case QVNT_H1:
+    case QVNT_Z: case QVNT_S: case QVNT_T: case QVNT_RZ:
+        return pc64(p.d.a) == 1;
+    case QVNT_RZZ:
+        return true;
+    default:
+        return false;
+    }
+}
+
 struct MInfo { int src; int form, ra, rb; };   // host-side description of every MOp (describe / tests)
 
 struct Plan {
@@ -205,6 +254,7 @@ struct Plan {
 // slot, two-bit ops (rxx/ryy, swap family, h2/u2) must sit on the slot pair (0,1) or (2,3)
 // because the interpreter only carries bodies for those (tile.cu).
 struct Slots {
+    uint64_t banned = 0; // bits a lazy x of this stage tests or flips: they must stay thread bits
     int bit[TILE_R];     // global bit held by slot j, -1 = free
     int find(int q) const {
         for (int j = 0; j < TILE_R; ++j)
@@ -219,6 +269,7 @@ static bool place_op(const POp &p, Slots &sl, int &ra, int &rb) {
     if (pc64(p.mix) == 1) {
         const int q = ctz64(p.mix);
         int j = sl.find(q);
+        if (j < 0 && ((sl.banned >> q) & 1)) return false;
         if (j < 0) {
             // prefer a free slot whose pair partner is already taken (keeps whole pairs free)
             for (int k = TILE_R - 1; k >= 0 && j < 0; --k)
@@ -241,6 +292,7 @@ static bool place_op(const POp &p, Slots &sl, int &ra, int &rb) {
         y = ctz64(p.mix & (p.mix - 1));
     }
     int jx = sl.find(x), jy = sl.find(y);
+    if ((jx < 0 && ((sl.banned >> x) & 1)) || (jy < 0 && ((sl.banned >> y) & 1))) return false;
     if (jx >= 0 && jy >= 0) {
         if ((jx ^ jy) != 1) return false;
     } else if (jx >= 0) {
@@ -268,16 +320,41 @@ static bool place_op(const POp &p, Slots &sl, int &ra, int &rb) {
 
 struct StageSel { int idx, ra, rb; };
 
+// lazy_x (fast passes): an x whose target and controls are not register-slot bits runs as a
+// permutation between threads (FC_LX, tile.cu) -- three integer instructions instead of 48-96
+// register moves.  Such an x is therefore DEFERRED while one of its bits sits in a slot and other
+// work remains to form a later stage; once placed, its bits are banned from becoming slots.
 static void stage_select(const std::vector<POp> &pl, const std::vector<int> &cand, uint64_t tile_set,
-                         size_t max_ops, std::vector<StageSel> &sel, std::vector<int> &rest, Slots &sl) {
+                         size_t max_ops, std::vector<StageSel> &sel, std::vector<int> &rest, Slots &sl,
+                         bool lazy_x) {
     for (int j = 0; j < TILE_R; ++j) sl.bit[j] = -1;
+    sl.banned = 0;
     uint64_t bw = 0, br = 0;
     sel.clear();
     rest.clear();
+    // later_work[i]: some op after cand[i] is not an x (so a later stage will exist anyway)
+    std::vector<char> later_work(cand.size() + 1, 0);
+    for (size_t k = cand.size(); k-- > 0;)
+        later_work[k] = later_work[k + 1] || pl[cand[k]].d.kind != QVNT_X;
     size_t i = 0;
     for (; i < cand.size(); ++i) {
         const POp &p = pl[cand[i]];
         bool conflict = (p.mix & (bw | br)) || (p.dg & bw) || sel.size() >= max_ops;
+        if (!conflict && lazy_x && p.d.kind == QVNT_X && pc64(p.mix) == 1) {
+            uint64_t slot_bits = 0;
+            for (int j = 0; j < TILE_R; ++j)
+                if (sl.bit[j] >= 0) slot_bits |= 1ull << sl.bit[j];
+            const uint64_t bits = p.mix | p.d.ctrl;
+            // (the TILE_R slots are always filled: enough unbanned tile bits must remain)
+            const bool room = pc64(tile_set) - pc64((sl.banned | bits) & tile_set) >= TILE_R;
+            if (!(bits & slot_bits) && room) {
+                sl.banned |= bits & tile_set;
+                sel.push_back({cand[i], -1, -1});
+                continue;
+            }
+            if (getenv("QVNT_LAZYX_DEFER") && (bits & slot_bits) && room && (later_work[i + 1] || !rest.empty()))
+                conflict = true;                                          // wait for a stage where it is lazy
+        }
         if (!conflict) {
             Slots trial = sl;
             int ra, rb;
@@ -308,10 +385,10 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
     uint32_t wbits = 0;
     while ((1u << wbits) < c.world) ++wbits;
 
-    uint32_t T = c.tile_bits ? (uint32_t)c.tile_bits : (uint32_t)TILE_MAX_BITS;
+    uint32_t T = c.tile_bits ? (uint32_t)c.tile_bits : (uint32_t)TILE_DEFAULT_BITS;
     if (T > (uint32_t)TILE_MAX_BITS) T = TILE_MAX_BITS;
-    if (T > n_local + (peers ? wbits : 0)) T = n_local + (peers ? wbits : 0);
-    uint32_t L = c.chunk_bits ? (uint32_t)c.chunk_bits : 7u;
+    if (T > n_local) T = n_local;      // (a tile with k rank bits pins k local bits outside the tile)
+    uint32_t L = c.chunk_bits ? (uint32_t)c.chunk_bits : (uint32_t)TILE_DEFAULT_CHUNK;
     if (L > n_local) L = n_local;
     if (L > T) L = T;
     if (T - L > (uint32_t)TILE_MAX_HIGH) L = T - TILE_MAX_HIGH;
@@ -434,7 +511,10 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
         }
         h.fx_val = h.fx.val;
 
+        bool pass_fast = true;
+        for (int idx : pp.ops) pass_fast = pass_fast && fast_kind(pl[idx]);
         PassPlan cur = pp;           // same geometry; ops / stages filled below (split if too long)
+        cur.hdr.full = pass_fast ? 0u : 1u;
         cur.ops.clear();
         cur.hdr.stage_begin = (uint32_t)plan.stages.size();
         cur.hdr.op_begin = (uint32_t)plan.mops.size();
@@ -445,7 +525,6 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                 cur.hdr.stage_end[k] = (uint16_t)(plan.stages[cur.hdr.stage_begin + k].op_end - cur.hdr.op_begin);
             if (cur.hdr.n_ops) out_passes.push_back(cur);
             cur.ops.clear();
-            cur.hdr.full = 0;
             cur.hdr.stage_begin = (uint32_t)plan.stages.size();
             cur.hdr.op_begin = (uint32_t)plan.mops.size();
         };
@@ -454,7 +533,7 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
         while (!c2.empty()) {
             Slots sl;
             const size_t room = (size_t)TILE_MAX_OPS - (plan.mops.size() - cur.hdr.op_begin);
-            stage_select(pl, c2, set, room, s2, r2, sl);
+            stage_select(pl, c2, set, room, s2, r2, sl, pass_fast && !getenv("QVNT_NO_LAZYX"));
             if (s2.empty() || plan.stages.size() - cur.hdr.stage_begin >= (size_t)TILE_MAX_STAGES) {
                 if (plan.mops.size() == cur.hdr.op_begin) {
                     set_error("internal: stage construction stalled");
@@ -470,7 +549,7 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
             for (int j = 0; j < TILE_R; ++j) {
                 if (sl.bit[j] >= 0) continue;
                 for (int l = (int)h.T - 1; l >= 0; --l)
-                    if (!((rset >> h.gpos[l]) & 1)) {
+                    if (!(((rset | sl.banned) >> h.gpos[l]) & 1)) {
                         sl.bit[j] = h.gpos[l];
                         rset |= 1ull << h.gpos[l];
                         break;
@@ -529,7 +608,48 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                 mi.src = ss.idx;
                 mi.ra = ss.ra;
                 mi.rb = ss.rb;
-                if (p.cls == CLS_DIAG) {
+                if (pass_fast) {
+                    const double c = p.d.ph_re, sn = p.d.ph_im, h = QV_FRAC_1_SQRT_2;
+                    const bool dg = p.d.dagger != 0;
+                    double f0r = 1.0, f0i = 0.0, f1r = 1.0, f1i = 0.0;
+                    mi.form = p.cls == CLS_DIAG ? TF_DIAG : TF_PAIR1;
+                    switch (p.d.kind) {
+                    case QVNT_H1: m.code = (uint8_t)(FC_PA + ss.ra); m.ph_re = c; break;
+                    case QVNT_RY: m.code = (uint8_t)(FC_PR + ss.ra); m.ph_re = c; m.ph_im = -sn; m.c2 = sn; m.c3 = c; break;
+                    case QVNT_RX: m.code = (uint8_t)(FC_PX + ss.ra); m.ph_re = c; m.ph_im = sn; m.c2 = sn; m.c3 = c; break;
+                    case QVNT_Y: m.code = (uint8_t)(FC_PX + ss.ra); m.ph_re = 0.0; m.ph_im = 1.0; m.c2 = -1.0; m.c3 = 0.0; break;
+                    case QVNT_X:
+                        if (ss.ra < 0) {
+                            uint32_t treg, tthr;
+                            uint64_t tbase;
+                            split(p.d.a, treg, tthr, tbase);
+                            m.code = (uint8_t)FC_LX;
+                            m.a_thr = tthr;
+                            m.a_reg = (uint16_t)lpos_of[ctz64(p.d.a)];
+                            mi.form = TF_LAZYX;
+                            mi.ra = mi.rb = 0;
+                        } else {
+                            m.code = (uint8_t)(FC_SW + ss.ra);
+                        }
+                        break;
+                    case QVNT_Z: f1r = -1.0; break;
+                    case QVNT_S: f1r = 0.0; f1i = dg ? -1.0 : 1.0; break;
+                    case QVNT_T: f1r = h; f1i = dg ? -h : h; break;
+                    default: f0r = c; f0i = -sn; f1r = c; f1i = sn; break;      // rz, rzz
+                    }
+                    if (p.cls == CLS_DIAG) {
+                        uint32_t areg, athr;
+                        split(p.d.a, areg, athr, b.a_base);
+                        m.a_reg = (uint16_t)areg;
+                        m.a_thr = athr;
+                        m.code = areg == 0 ? (uint8_t)FC_DU
+                                 : pc64(areg) == 1 ? (uint8_t)(FC_DS + ctz64(areg)) : (uint8_t)FC_DG;
+                        m.ph_re = f0r; m.ph_im = f0i; m.c2 = f1r; m.c3 = f1i;
+                        if (f0r == 1.0 && f0i == 0.0) m.dagger |= MOP_SKIP0;
+                        mi.ra = mi.rb = 0;
+                    }
+                    if (m.okmask == 0xFFFFu && m.code != (uint8_t)FC_LX) m.code = (uint8_t)(m.code + FC_ALL);
+                } else if (p.cls == CLS_DIAG) {
                     uint32_t areg, athr;
                     split(p.d.a, areg, athr, b.a_base);
                     m.a_reg = (uint16_t)areg;
@@ -579,7 +699,6 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                         return QVNT_ERR_INVALID;
                     }
                 }
-                if (m.code >= MC_P1 + 20) cur.hdr.full = 1;      // u1 and everything after it in MCode
                 plan.mops.push_back(m);
                 plan.bases.push_back(b);
                 plan.minfo.push_back(mi);

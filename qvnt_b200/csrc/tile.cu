@@ -250,101 +250,347 @@ __device__ __forceinline__ void apply_mop(const MDec &m, const uint32_t fl, cons
     }
 }
 
-// One stage on one tile: every thread takes the 16 amplitudes of its group(s) into registers,
-// runs the stage's ops on them and writes them back.  All addresses are 32-bit shared-window
-// offsets; the op range [ob, oe) is relative to the pass's first op.
-template <bool FULL>
-__device__ __forceinline__ void run_stage(const uint32_t tile_s, const uint32_t stage_s, const uint32_t ops_s,
-                                          const uint32_t flags_s, const uint32_t ob, const uint32_t oe,
-                                          const uint32_t n_t, const amp *__restrict__ mats) {
+// ---- stage plumbing shared by both interpreters ------------------------------------------------
+// A stage gives the thread of group `grp` the 16 amplitudes whose tile-local indices are
+// jl ^ (subset of the 4 register-slot bits).  All shared-memory addresses are 32-bit
+// shared-window offsets, XOR-swizzled (swz is GF(2)-linear: address(K) = mine_o ^ c[..]).
+struct StageCtx {
+    uint32_t r_lpos;    // 4 bytes: register slot j -> tile-local bit position
+    uint32_t c[TR];     // swizzled byte offsets of the 4 register-slot bits
+    uint32_t jl;        // tile-local index of slot pattern 0
+    uint32_t mine_o;    // its swizzled byte offset
+};
+
+__device__ __forceinline__ StageCtx stage_ctx(const uint32_t stage_s, const uint32_t n_t, const uint32_t grp) {
     uint32_t sw[8];      // the TStage: op_begin, op_end, r_lpos[4], t_lpos[16], pad
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
                  : "=r"(sw[0]), "=r"(sw[1]), "=r"(sw[2]), "=r"(sw[3]) : "r"(stage_s) : "memory");
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
                  : "=r"(sw[4]), "=r"(sw[5]), "=r"(sw[6]), "=r"(sw[7]) : "r"(stage_s + 16u) : "memory");
-    uint32_t c[TR];
+    StageCtx x;
+    x.r_lpos = sw[2];
 #pragma unroll
-    for (int j = 0; j < TR; ++j) c[j] = 16u * swz(1u << ((sw[2] >> (8 * j)) & 0xFFu));
-    const uint32_t groups = 1u << n_t;
-    for (uint32_t grp = threadIdx.x; grp < groups; grp += blockDim.x) {
-        uint32_t jl = 0;
+    for (int j = 0; j < TR; ++j) x.c[j] = 16u * swz(1u << ((sw[2] >> (8 * j)) & 0xFFu));
+    uint32_t jl = 0;
 #pragma unroll
-        for (uint32_t k = 0; k < 16; ++k) {
-            if (k < n_t) jl |= ((grp >> k) & 1u) << ((sw[3 + (k >> 2)] >> (8 * (k & 3))) & 0xFFu);
-        }
-        const uint32_t mine_o = 16u * swz(jl);      // byte offset of slot pattern 0 in the tile
-        // (the XOR applies to the offset inside the tile: the tile itself is only 16-byte aligned)
-        amp v[NV];
+    for (uint32_t k = 0; k < 16; ++k) {
+        if (k < n_t) jl |= ((grp >> k) & 1u) << ((sw[3 + (k >> 2)] >> (8 * (k & 3))) & 0xFFu);
+    }
+    x.jl = jl;
+    x.mine_o = 16u * swz(jl);
+    return x;
+}
+
+__device__ __forceinline__ void stage_load(const uint32_t tile_s, const StageCtx &x, amp (&v)[NV]) {
 #pragma unroll
-        for (int K = 0; K < NV; ++K) {
-            uint32_t a = mine_o;
-            if (K & 1) a ^= c[0];
-            if (K & 2) a ^= c[1];
-            if (K & 4) a ^= c[2];
-            if (K & 8) a ^= c[3];
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n"
-                         : "=d"(v[K].x), "=d"(v[K].y)
-                         : "r"(tile_s + a)
-                         : "memory");
-        }
-        // ob / oe come from the kernel parameters (uniform registers): the loop control costs no
-        // vector registers, which the arms below need for their 16 amplitudes + products.
-        // The descriptor of op o+1 is fetched before op o's arithmetic is issued, so its
-        // shared-memory latency hides under the FP64 burst of op o.
-        MDec m_nx;
-        uint32_t fl_nx;
-        auto fetch = [&](uint32_t o) {
-            const uint32_t op_a = ops_s + 32u * o, fl_a = flags_s + o;
-            asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(fl_nx) : "r"(fl_a) : "memory");
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
-                         : "=r"(m_nx.w0), "=r"(m_nx.ctrl_thr), "=r"(m_nx.a_thr), "=r"(m_nx.a_reg)
-                         : "r"(op_a)
-                         : "memory");
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n"
-                         : "=d"(m_nx.ph_re), "=d"(m_nx.ph_im)
-                         : "r"(op_a + 16u)
-                         : "memory");
-        };
-        if (ob < oe) fetch(ob);
-        for (uint32_t o = ob; o < oe; ++o) {
-            const MDec m = m_nx;
-            const uint32_t fl = fl_nx;
-#if QV_OP_PREFETCH
+    for (int K = 0; K < NV; ++K) {
+        uint32_t a = x.mine_o;
+        if (K & 1) a ^= x.c[0];
+        if (K & 2) a ^= x.c[1];
+        if (K & 4) a ^= x.c[2];
+        if (K & 8) a ^= x.c[3];
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v[K].x), "=d"(v[K].y) : "r"(tile_s + a) : "memory");
+    }
+}
+
+__device__ __forceinline__ void stage_store_smem(const uint32_t tile_s, const StageCtx &x, const amp (&v)[NV]) {
+#pragma unroll
+    for (int K = 0; K < NV; ++K) {
+        uint32_t a = x.mine_o;
+        if (K & 1) a ^= x.c[0];
+        if (K & 2) a ^= x.c[1];
+        if (K & 4) a ^= x.c[2];
+        if (K & 8) a ^= x.c[3];
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(tile_s + a), "d"(v[K].x), "d"(v[K].y) : "memory");
+    }
+}
+
+// Last stage of a pass: the 16 amplitudes go straight from registers to HBM (or to the peer's
+// HBM): address = chunk base pointer (tile-invariant table) + this tile's byte offset + offset
+// inside the chunk.  The planner makes the low lane bits the lowest tile-local bits that are not
+// register slots, so a warp's store instruction covers up to 512 contiguous bytes.
+__device__ __forceinline__ void stage_store_global(const uint32_t ptr0_s, const uint32_t L,
+                                                   const unsigned long long toff, const StageCtx &x,
+                                                   const amp (&v)[NV]) {
+    uint32_t offc[TR], chc[TR];       // per register slot: its bit inside the chunk / in the chunk index
+#pragma unroll
+    for (int j = 0; j < TR; ++j) {
+        const uint32_t lp = (x.r_lpos >> (8 * j)) & 0xFFu;
+        offc[j] = lp < L ? (16u << lp) : 0u;
+        chc[j] = lp < L ? 0u : (8u << (lp - L));
+    }
+    const unsigned long long off0 = toff + (x.jl & ((1u << L) - 1u)) * 16u;
+    const uint32_t ch0 = ptr0_s + (x.jl >> L) * 8u;
+#pragma unroll
+    for (int K = 0; K < NV; ++K) {
+        uint32_t off = 0, ch = ch0;
+        if (K & 1) { off |= offc[0]; ch += chc[0]; }      // (ch is an address: add, the table is not
+        if (K & 2) { off |= offc[1]; ch += chc[1]; }      //  aligned to its own size)
+        if (K & 4) { off |= offc[2]; ch += chc[2]; }
+        if (K & 8) { off |= offc[3]; ch += chc[3]; }
+        unsigned long long base;
+        asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(base) : "r"(ch) : "memory");
+        *reinterpret_cast<amp *>(base + off0 + off) = v[K];
+    }
+}
+
+// The op loop of the FULL interpreter: ops [ob, oe) of the pass on the register-resident amplitudes.
+__device__ __forceinline__ void stage_ops_full(const uint32_t ops_s, const uint32_t flags_s, const uint32_t ob,
+                                               const uint32_t oe, const uint32_t grp,
+                                               const amp *__restrict__ mats, amp (&v)[NV]) {
+    // The descriptor of op o+1 is fetched before op o's arithmetic is issued, so its
+    // shared-memory latency hides under the FP64 burst of op o.
+    MDec m_nx;
+    uint32_t fl_nx;
+    auto fetch = [&](uint32_t o) {
+        const uint32_t op_a = ops_s + MOP_BYTES * o, fl_a = flags_s + o;
+        asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(fl_nx) : "r"(fl_a) : "memory");
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+                     : "=r"(m_nx.w0), "=r"(m_nx.ctrl_thr), "=r"(m_nx.a_thr), "=r"(m_nx.a_reg)
+                     : "r"(op_a)
+                     : "memory");
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n"
+                     : "=d"(m_nx.ph_re), "=d"(m_nx.ph_im)
+                     : "r"(op_a + 16u)
+                     : "memory");
+    };
+    if (ob < oe) fetch(ob);
+    for (uint32_t o = ob; o < oe; ++o) {
+        const MDec m = m_nx;
+        const uint32_t fl = fl_nx;
+        if (!(fl & 0x80u) || (~grp & m.ctrl_thr)) {
             if (o + 1 < oe) fetch(o + 1);
-#endif
-            if (!(fl & 0x80u) || (~grp & m.ctrl_thr)) {
-#if !QV_OP_PREFETCH
-                if (o + 1 < oe) fetch(o + 1);
-#endif
-                continue;
-            }
-            if ((m.w0 >> 16) == 0xFFFFu) apply_mop<true, FULL>(m, fl, grp, mats, v);
-            else apply_mop<false, FULL>(m, fl, grp, mats, v);
-#if !QV_OP_PREFETCH
-            if (o + 1 < oe) fetch(o + 1);
-#endif
+            continue;
         }
-        // recompute the 16 slot addresses instead of keeping them live across the op loop
-        uint32_t mine_o2 = mine_o;
-        asm volatile("" : "+r"(mine_o2));
-#pragma unroll
-        for (int K = 0; K < NV; ++K) {
-            uint32_t a = mine_o2;
-            if (K & 1) a ^= c[0];
-            if (K & 2) a ^= c[1];
-            if (K & 4) a ^= c[2];
-            if (K & 8) a ^= c[3];
-            asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(tile_s + a), "d"(v[K].x), "d"(v[K].y)
-                         : "memory");
+        if ((m.w0 >> 16) == 0xFFFFu) apply_mop<true, true>(m, fl, grp, mats, v);
+        else apply_mop<false, true>(m, fl, grp, mats, v);
+        if (o + 1 < oe) fetch(o + 1);
+    }
+}
+
+// ================================================================================================
+// FAST stage interpreter.  Passes made only of the common kinds are lowered by the planner to the
+// coefficient-driven forms of FCode (engine.h); every arm below updates the 16 register-resident
+// amplitudes IN PLACE through inline PTX whose operands are tied ("+d"), so each amplitude keeps
+// one home register through the whole op loop: no register shuffling at the merge points of the
+// dispatch, no selects -- per op the instruction stream is the FP64 arithmetic plus ~15
+// instructions of fetch / test / dispatch.  4 FP64 instructions per amplitude and op
+// (2 mul + 2 fma), the same count as the reference formulas with contraction.
+// ================================================================================================
+__device__ __forceinline__ void f_pair_real(amp &p0, amp &p1, double a, double b, double c, double d) {
+    asm volatile("{\n\t.reg .f64 t, u, w, z;\n\t"
+                 "mul.rn.f64 t, %4, %0;\n\t"
+                 "mul.rn.f64 u, %6, %0;\n\t"
+                 "mul.rn.f64 w, %4, %1;\n\t"
+                 "mul.rn.f64 z, %6, %1;\n\t"
+                 "fma.rn.f64 %0, %5, %2, t;\n\t"
+                 "fma.rn.f64 %1, %5, %3, w;\n\t"
+                 "fma.rn.f64 %2, %7, %2, u;\n\t"
+                 "fma.rn.f64 %3, %7, %3, z;\n\t}"
+                 : "+d"(p0.x), "+d"(p0.y), "+d"(p1.x), "+d"(p1.y)
+                 : "d"(a), "d"(b), "d"(c), "d"(d));
+}
+// new0 = (p0 + p1) * s ; new1 = (p0 - p1) * s
+__device__ __forceinline__ void f_pair_addsub(amp &p0, amp &p1, double sc) {
+    asm volatile("{\n\t.reg .f64 t, u, w, z;\n\t"
+                 "add.rn.f64 t, %0, %2;\n\t"
+                 "sub.rn.f64 u, %0, %2;\n\t"
+                 "add.rn.f64 w, %1, %3;\n\t"
+                 "sub.rn.f64 z, %1, %3;\n\t"
+                 "mul.rn.f64 %0, t, %4;\n\t"
+                 "mul.rn.f64 %2, u, %4;\n\t"
+                 "mul.rn.f64 %1, w, %4;\n\t"
+                 "mul.rn.f64 %3, z, %4;\n\t}"
+                 : "+d"(p0.x), "+d"(p0.y), "+d"(p1.x), "+d"(p1.y)
+                 : "d"(sc));
+}
+// new0 = a*p0 - i*b*p1 ; new1 = -i*c*p0 + d*p1   (nb = -b, nc = -c)
+__device__ __forceinline__ void f_pair_cross(amp &p0, amp &p1, double a, double b, double nb, double c, double nc,
+                                             double d) {
+    asm volatile("{\n\t.reg .f64 t, u, w, z;\n\t"
+                 "mul.rn.f64 t, %4, %0;\n\t"      // a * p0.x
+                 "mul.rn.f64 w, %4, %1;\n\t"      // a * p0.y
+                 "mul.rn.f64 u, %7, %1;\n\t"      // c * p0.y
+                 "mul.rn.f64 z, %8, %0;\n\t"      // -c * p0.x
+                 "fma.rn.f64 %0, %5, %3, t;\n\t"  // p0.x = b * p1.y + a * p0.x
+                 "fma.rn.f64 %1, %6, %2, w;\n\t"  // p0.y = -b * p1.x + a * p0.y
+                 "fma.rn.f64 %2, %9, %2, u;\n\t"  // p1.x = d * p1.x + c * p0.y
+                 "fma.rn.f64 %3, %9, %3, z;\n\t}" // p1.y = d * p1.y - c * p0.x
+                 : "+d"(p0.x), "+d"(p0.y), "+d"(p1.x), "+d"(p1.y)
+                 : "d"(a), "d"(b), "d"(nb), "d"(c), "d"(nc), "d"(d));
+}
+__device__ __forceinline__ void f_swap(amp &p0, amp &p1) {
+    asm volatile("{\n\t.reg .f64 t, u;\n\t"
+                 "mov.f64 t, %0;\n\t"
+                 "mov.f64 u, %1;\n\t"
+                 "mov.f64 %0, %2;\n\t"
+                 "mov.f64 %1, %3;\n\t"
+                 "mov.f64 %2, t;\n\t"
+                 "mov.f64 %3, u;\n\t}"
+                 : "+d"(p0.x), "+d"(p0.y), "+d"(p1.x), "+d"(p1.y));
+}
+// p *= (fr, fi)   (nfi = -fi)
+__device__ __forceinline__ void f_cmul(amp &p, double fr, double fi, double nfi) {
+    asm volatile("{\n\t.reg .f64 t, u;\n\t"
+                 "mul.rn.f64 t, %4, %1;\n\t"      // -fi * y
+                 "mul.rn.f64 u, %3, %0;\n\t"      //  fi * x
+                 "fma.rn.f64 %0, %2, %0, t;\n\t"  // x = fr * x - fi * y
+                 "fma.rn.f64 %1, %2, %1, u;\n\t}" // y = fr * y + fi * x
+                 : "+d"(p.x), "+d"(p.y)
+                 : "d"(fr), "d"(fi), "d"(nfi));
+}
+
+struct FDec {
+    uint32_t w0;        // code | flags << 8 | okmask << 16
+    uint32_t ctrl_thr;
+    uint32_t a_thr;
+    uint32_t a_reg;     // low 16 bits
+    double c0, c1, c2, c3;
+};
+
+template <int RB, bool ALL>
+__device__ __forceinline__ void farm_pr(amp (&v)[NV], const FDec &m, const uint32_t ok) {
+    QV_FOR_K {
+        if (K & (1 << RB)) continue;
+        if (ALL || ((ok >> K) & 1u)) f_pair_real(v[K], v[K | (1 << RB)], m.c0, m.c1, m.c2, m.c3);
+    }
+}
+template <int RB, bool ALL>
+__device__ __forceinline__ void farm_pa(amp (&v)[NV], const FDec &m, const uint32_t ok) {
+    QV_FOR_K {
+        if (K & (1 << RB)) continue;
+        if (ALL || ((ok >> K) & 1u)) f_pair_addsub(v[K], v[K | (1 << RB)], m.c0);
+    }
+}
+template <int RB, bool ALL>
+__device__ __forceinline__ void farm_px(amp (&v)[NV], const FDec &m, const uint32_t ok) {
+    const double nb = -m.c1, nc = -m.c2;
+    QV_FOR_K {
+        if (K & (1 << RB)) continue;
+        if (ALL || ((ok >> K) & 1u)) f_pair_cross(v[K], v[K | (1 << RB)], m.c0, m.c1, nb, m.c2, nc, m.c3);
+    }
+}
+template <int RB, bool ALL>
+__device__ __forceinline__ void farm_sw(amp (&v)[NV], const uint32_t ok) {
+    QV_FOR_K {
+        if (K & (1 << RB)) continue;
+        if (ALL || ((ok >> K) & 1u)) f_swap(v[K], v[K | (1 << RB)]);
+    }
+}
+// diagonal, no target bit in a register slot: one factor for the whole thread
+template <bool ALL>
+__device__ __forceinline__ void farm_du(amp (&v)[NV], const FDec &m, const uint32_t ok, const uint32_t par) {
+    if (!par && (m.w0 & ((uint32_t)MOP_SKIP0 << 8))) return;
+    const double fr = par ? m.c2 : m.c0, fi = par ? m.c3 : m.c1, nfi = -fi;
+    QV_FOR_K {
+        if (ALL || ((ok >> K) & 1u)) f_cmul(v[K], fr, fi, nfi);
+    }
+}
+// diagonal, exactly one target bit in register slot RB (+ parity `par` of the target bits elsewhere)
+template <int RB, bool ALL>
+__device__ __forceinline__ void farm_ds(amp (&v)[NV], const FDec &m, const uint32_t ok, const uint32_t par) {
+    double f0r = m.c0, f0i = m.c1, f1r = m.c2, f1i = m.c3;
+    bool skip0 = (m.w0 & ((uint32_t)MOP_SKIP0 << 8)) != 0;
+    if (par) {                    // rzz with its second bit outside the slots: the roles swap
+        f0r = m.c2; f0i = m.c3; f1r = m.c0; f1i = m.c1;
+        skip0 = false;
+    }
+    const double n0 = -f0i, n1 = -f1i;
+    if (!skip0) {
+        QV_FOR_K {
+            if (K & (1 << RB)) continue;
+            if (ALL || ((ok >> K) & 1u)) f_cmul(v[K], f0r, f0i, n0);
+        }
+    }
+    QV_FOR_K {
+        if (!(K & (1 << RB))) continue;
+        if (ALL || ((ok >> K) & 1u)) f_cmul(v[K], f1r, f1i, n1);
+    }
+}
+// diagonal, any set of target bits in register slots (rare: rzz with both bits in slots)
+__device__ __forceinline__ void farm_dg(amp (&v)[NV], const FDec &m, const uint32_t ok, const uint32_t par) {
+    const uint32_t a_reg = m.a_reg & 0xFu;
+    const double n0 = -m.c1, n1 = -m.c3;
+    QV_FOR_K {
+        if ((ok >> K) & 1u) {
+            if ((__popc((uint32_t)K & a_reg) + par) & 1u) f_cmul(v[K], m.c2, m.c3, n1);
+            else f_cmul(v[K], m.c0, m.c1, n0);
         }
     }
 }
 
+#define QV_F4(ARM, ALLV, base, ...)                                    \
+    case base + 0: ARM<0, ALLV>(__VA_ARGS__); break;                   \
+    case base + 1: ARM<1, ALLV>(__VA_ARGS__); break;                   \
+    case base + 2: ARM<2, ALLV>(__VA_ARGS__); break;                   \
+    case base + 3: ARM<3, ALLV>(__VA_ARGS__); break;
+
+// One jump table over (form, slot, "no control sits in a register slot"): the planner adds
+// FC_ALL to the code when okmask == 0xFFFF, so the common case runs without per-slot predicates.
+__device__ __forceinline__ void apply_fop(const FDec &m, const uint32_t fl, const uint32_t grp, amp (&v)[NV]) {
+    const uint32_t ok = m.w0 >> 16;
+    uint32_t code = m.w0 & 0xFFu;
+    asm volatile("" : "+r"(code));
+    switch (code) {
+    QV_F4(farm_pr, false, FC_PR, v, m, ok)
+    QV_F4(farm_px, false, FC_PX, v, m, ok)
+    QV_F4(farm_sw, false, FC_SW, v, ok)
+    case FC_DU: farm_du<false>(v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u); break;
+    QV_F4(farm_ds, false, FC_DS, v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u)
+    case FC_DG: farm_dg(v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u); break;
+    QV_F4(farm_pa, false, FC_PA, v, m, ok)
+    QV_F4(farm_pr, true, FC_ALL + FC_PR, v, m, ok)
+    QV_F4(farm_px, true, FC_ALL + FC_PX, v, m, ok)
+    QV_F4(farm_sw, true, FC_ALL + FC_SW, v, ok)
+    case FC_ALL + FC_DU: farm_du<true>(v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u); break;
+    QV_F4(farm_ds, true, FC_ALL + FC_DS, v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u)
+    case FC_ALL + FC_DG: farm_dg(v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u); break;
+    QV_F4(farm_pa, true, FC_ALL + FC_PA, v, m, ok)
+    default: break;
+    }
+}
+
+// The op loop of the FAST interpreter.
+// FC_LX ("lazy x"): an x whose target and controls all sit on thread / outer bits is a permutation
+// BETWEEN threads: it costs three XORs -- the thread flips the bit in the index it will store its
+// amplitudes to (x.jl / x.mine_o) and in the virtual group number `vgrp` the later ops of the
+// stage test their thread-bit controls and parities against.
+__device__ __forceinline__ void stage_ops_fast(const uint32_t ops_s, const uint32_t flags_s, const uint32_t ob,
+                                               const uint32_t oe, const uint32_t grp, StageCtx &x, amp (&v)[NV]) {
+    uint32_t vgrp = grp;
+    for (uint32_t o = ob; o < oe; ++o) {
+        const uint32_t op_a = ops_s + MOP_BYTES * o;
+        uint32_t fl;
+        FDec m;
+        asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(fl) : "r"(flags_s + o) : "memory");
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+                     : "=r"(m.w0), "=r"(m.ctrl_thr), "=r"(m.a_thr), "=r"(m.a_reg)
+                     : "r"(op_a)
+                     : "memory");
+        if (!(fl & 0x80u) || (~vgrp & m.ctrl_thr)) continue;
+        if ((m.w0 & 0xFFu) == (uint32_t)FC_LX) {
+            vgrp ^= m.a_thr;
+            x.jl ^= 1u << (m.a_reg & 0xFFu);
+            x.mine_o ^= 16u * swz(1u << (m.a_reg & 0xFFu));
+            continue;
+        }
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(m.c0), "=d"(m.c1) : "r"(op_a + 16u) : "memory");
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(m.c2), "=d"(m.c3) : "r"(op_a + 32u) : "memory");
+        apply_fop(m, fl, vgrp, v);
+    }
+}
+
 // Kernel configurations: <threads per CTA, min CTAs per SM, tile buffers>.
-//   T <= 11: 128 threads, 3 CTAs/SM, TWO tile buffers -- the next tile's cp.async loads are in
-//            flight while the current tile is computed, stores are fire-and-forget, so the HBM
-//            phases overlap the FP64 phases inside each CTA.
-//   T == 12: 256 threads, 2 CTAs/SM, one 64 KiB buffer (two do not fit twice per SM).
+//   T == 12: 256 threads, 2 CTAs/SM, one 64 KiB buffer.  The last stage stores its registers
+//            straight to HBM, so the buffer is free as soon as that stage has read it: the next
+//            tile's cp.async loads are issued right there and overlap the last stage's arithmetic
+//            and stores.
+//   T <= 11: 128 threads, 4 CTAs/SM, one 32 KiB buffer each (default): the kernel is bound by
+//            instruction issue and latency, not by HBM, so the extra resident warps pay more
+//            than a second buffer does (option "tile_nbuf" = 2: 3 CTAs/SM with two buffers).
+constexpr uint32_t META_SLOTS = 3;      // per-tile op flags rotate through 3 slots: preparing tile i+1 must not
+                                        // race with the threads still running the ops of tile i-1
+
 template <int THREADS, int MINB, int NB, bool FULL>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr hdr,
@@ -362,119 +608,151 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
 
     // shared memory carve-up (16-byte aligned sections first)
     unsigned char *tiles_b = smem_raw;                                            // NB * (16 << T)
-    MOp *s_ops = reinterpret_cast<MOp *>(smem_raw + (size_t)NB * tile_bytes);      // 32 * n_ops
+    MOp *s_ops = reinterpret_cast<MOp *>(smem_raw + (size_t)NB * tile_bytes);      // 48 * n_ops
     TStage *s_stages = reinterpret_cast<TStage *>(s_ops + n_ops);                  // 32 * n_stages
-    amp **s_cptr_all = reinterpret_cast<amp **>(s_stages + n_stages);              // NB * 8 * n_chunks
-    uint8_t *s_flags_all = reinterpret_cast<uint8_t *>(s_cptr_all + NB * n_chunks);  // NB * flags_stride
+    MBase *s_bases = reinterpret_cast<MBase *>(s_stages + n_stages);               // 16 * n_ops
+    unsigned long long *s_ptr0 = reinterpret_cast<unsigned long long *>(s_bases + n_ops);   // 8 * n_chunks
+    uint8_t *s_flags_all = reinterpret_cast<uint8_t *>(s_ptr0 + n_chunks);         // 3 * flags_stride
 
+    const uint32_t shard_shift = segs.shift;
+    const uint64_t shard_mask = (1ull << shard_shift) - 1ull;
     // the pass program: same for every tile this CTA processes
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(g_ops + hdr.op_begin);
         uint4 *dst = reinterpret_cast<uint4 *>(s_ops);
-        for (uint32_t i = tid; i < 2 * n_ops; i += nthr) dst[i] = src[i];
+        for (uint32_t i = tid; i < (MOP_BYTES / 16u) * n_ops; i += nthr) dst[i] = src[i];
         src = reinterpret_cast<const uint4 *>(g_stages + hdr.stage_begin);
         dst = reinterpret_cast<uint4 *>(s_stages);
         for (uint32_t i = tid; i < 2 * n_stages; i += nthr) dst[i] = src[i];
+        src = reinterpret_cast<const uint4 *>(g_bases + hdr.op_begin);
+        dst = reinterpret_cast<uint4 *>(s_bases);
+        for (uint32_t i = tid; i < n_ops; i += nthr) dst[i] = src[i];
+        // Chunk base pointers for the tile at offset 0: chunk c = the 2^L amplitudes whose gathered
+        // tile bits spell c.  Rank bits among them select the shard (own HBM or a peer's, mapped
+        // over NVLink); every tile of the pass adds the same byte offset to all of them.
+        for (uint32_t c = tid; c < n_chunks; c += nthr) {
+            uint64_t gidx = hdr.base_or;
+            for (uint32_t j = 0; j < T - L; ++j)
+                if ((c >> j) & 1u) gidx |= 1ull << hdr.gpos[L + j];
+            s_ptr0[c] = (unsigned long long)(uintptr_t)(segs.seg[gidx >> shard_shift] + (gidx & shard_mask));
+        }
     }
-    const uint32_t shard_shift = segs.shift;
-    const uint64_t shard_mask = (1ull << shard_shift) - 1ull;
     const uint32_t n_t = T - TR;                     // thread bits per stage
-    const MBase *bases = g_bases + hdr.op_begin;
     const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(tiles_b);
     const uint32_t ops_s = (uint32_t)__cvta_generic_to_shared(s_ops);
     const uint32_t stages_s = (uint32_t)__cvta_generic_to_shared(s_stages);
     const uint32_t flags_all_s = (uint32_t)__cvta_generic_to_shared(s_flags_all);
+    const uint32_t ptr0_s = (uint32_t)__cvta_generic_to_shared(s_ptr0);
+    const bool active = tid < (1u << n_t);           // this thread owns a group of 16 amplitudes
     __syncthreads();
 
     // Metadata of the first tile >= t (stepping by the grid) that some op of this pass can change:
     // per-op flags (bit 7: controls outside the tile satisfied; bits 0-2: popcount of the diagonal
-    // target mask over the bits outside the tile, mod 8) and the chunk pointers.  Tiles no op
-    // touches (multi-controlled gates) are skipped without being read.  Returns n_tiles if none.
-    auto prepare = [&](uint64_t t, uint32_t slot) -> uint64_t {
+    // target mask over the bits outside the tile, mod 8) and the tile's byte offset inside the
+    // shard.  Tiles no op touches (multi-controlled gates) are skipped without being read.
+    // Returns n_tiles if there is none.
+    auto prepare = [&](uint64_t t, uint32_t slot, unsigned long long &toff) -> uint64_t {
         uint8_t *flags = s_flags_all + slot * flags_stride;
-        amp **cptr = s_cptr_all + slot * n_chunks;
         for (; t < hdr.n_tiles; t += gridDim.x) {
-            uint64_t base = t;               // tile counter -> global base index (tile bits clear)
+            uint64_t base = t;               // tile counter -> local base index (tile bits clear)
             for (uint32_t k = 0; k < hdr.n_runs; ++k) {
                 const uint32_t p = hdr.run_pos[k], len = hdr.run_len[k];
                 base = ((base >> p) << (p + len)) | (base & ((1ull << p) - 1ull));
             }
-            base |= hdr.fx_val | hdr.base_or;
+            base |= hdr.fx_val;
+            toff = base * 16ull;
+            base |= hdr.base_or;
             int any = 0;
             for (uint32_t o = tid; o < n_ops; o += nthr) {
-                const MBase b = bases[o];
+                const MBase b = s_bases[o];
                 const uint32_t okb = ((~base & b.ctrl_base) == 0) ? 0x80u : 0u;
                 flags[o] = (uint8_t)(okb | ((uint32_t)__popcll(base & b.a_base) & 7u));
                 any |= (int)okb;
-            }
-            for (uint32_t c = tid; c < n_chunks; c += nthr) {
-                uint64_t gidx = base;
-                for (uint32_t j = 0; j < T - L; ++j)
-                    if ((c >> j) & 1u) gidx |= 1ull << hdr.gpos[L + j];
-                cptr[c] = segs.seg[gidx >> shard_shift] + (gidx & shard_mask);
             }
             if (__syncthreads_or(any)) return t;
         }
         return hdr.n_tiles;
     };
-    // 2^(T-L) chunks of 2^L contiguous amplitudes, 16-byte cp.async, swizzled; one commit group
-    auto issue_load = [&](uint32_t slot) {
-        amp *const *cptr = s_cptr_all + slot * n_chunks;
-        unsigned char *tb = tiles_b + slot * tile_bytes;
-        for (uint32_t j = tid; j < tile_len; j += nthr) cp_async_16(tb + 16u * swz(j), cptr[j >> L] + (j & lmask));
+    // 2^(T-L) chunks of 2^L contiguous amplitudes, 16-byte cp.async, swizzled; one commit group.
+    // Element j = tid + i * nthr: swz is GF(2)-linear and the thread count a power of two, so the
+    // shared-memory slot is swz(tid) ^ swz(i * nthr); with nthr a multiple of the chunk length the
+    // offset inside the chunk is the thread's own and the chunk index advances by nthr >> L.
+    const uint32_t my_slot = 16u * swz(tid);
+    const bool regular = (nthr & lmask) == 0u && (tile_len % nthr) == 0u;
+    auto issue_load = [&](const unsigned long long toff, uint32_t bslot) {
+        const uint32_t tb_s = tiles_s + bslot * tile_bytes;
+        if (regular) {
+            const unsigned long long mine = toff + (unsigned long long)(tid & lmask) * 16ull;
+            const uint32_t cstep = (nthr >> L) * 8u;
+            uint32_t ch = ptr0_s + (tid >> L) * 8u;
+            for (uint32_t jb = 0; jb < tile_len; jb += nthr, ch += cstep) {
+                unsigned long long p;
+                asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(p) : "r"(ch) : "memory");
+                p += mine;
+                const uint32_t d = tb_s + (my_slot ^ (16u * swz(jb)));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(p) : "memory");
+            }
+        } else {
+            for (uint32_t j = tid; j < tile_len; j += nthr) {
+                const unsigned long long p = s_ptr0[j >> L] + toff + (unsigned long long)(j & lmask) * 16ull;
+                const uint32_t d = tb_s + 16u * swz(j);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(p) : "memory");
+            }
+        }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
 
-    uint32_t slot = 0;
-    uint64_t t_cur = prepare(blockIdx.x, slot);
-    if (t_cur < hdr.n_tiles) issue_load(slot);
+    uint32_t mslot = 0, bslot = 0;
+    unsigned long long toff_cur = 0, toff_next = 0;
+    uint64_t t_cur = prepare(blockIdx.x, mslot, toff_cur);
+    if (t_cur < hdr.n_tiles) issue_load(toff_cur, bslot);
     while (t_cur < hdr.n_tiles) {
-        uint64_t t_next = hdr.n_tiles;
-        if (NB == 2) {
-            t_next = prepare(t_cur + gridDim.x, slot ^ 1u);
-            if (t_next < hdr.n_tiles) {
-                issue_load(slot ^ 1u);
-                asm volatile("cp.async.wait_group 1;\n" ::: "memory");
-            } else {
-                asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-            }
+        const uint32_t mnext = mslot + 1u == META_SLOTS ? 0u : mslot + 1u;
+        const uint64_t t_next = prepare(t_cur + gridDim.x, mnext, toff_next);
+        const bool has_next = t_next < hdr.n_tiles;
+        if (NB == 2 && has_next) {
+            issue_load(toff_next, bslot ^ 1u);
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         }
         __syncthreads();
-        const uint32_t tile_s = tiles_s + slot * tile_bytes;
-        const uint32_t flags_s = flags_all_s + slot * flags_stride;
+        const uint32_t tile_s = tiles_s + bslot * tile_bytes;
+        const uint32_t flags_s = flags_all_s + mslot * flags_stride;
 
-        // ---- stages: 16 amplitudes per thread in registers ------------------------------------
         for (uint32_t s = 0; s < n_stages; ++s) {
-            run_stage<FULL>(tile_s, stages_s + 32u * s, ops_s, flags_s, s ? hdr.stage_end[s - 1] : 0u, hdr.stage_end[s],
-                      n_t, mats);
-            __syncthreads();
+            const bool last = s + 1 == n_stages;
+            const uint32_t ob = s ? hdr.stage_end[s - 1] : 0u, oe = hdr.stage_end[s];
+            amp v[NV];
+            StageCtx x;
+            if (active) {
+                x = stage_ctx(stages_s + 32u * s, n_t, tid);
+                stage_load(tile_s, x, v);
+            }
+            if (last && NB == 1) {
+                __syncthreads();                       // every thread holds its amplitudes: the buffer is free
+                if (has_next) issue_load(toff_next, bslot);
+            }
+            if (active) {
+                if (FULL) stage_ops_full(ops_s, flags_s, ob, oe, tid, mats, v);
+                else stage_ops_fast(ops_s, flags_s, ob, oe, tid, x, v);
+                if (last) stage_store_global(ptr0_s, L, toff_cur, x, v);
+                else stage_store_smem(tile_s, x, v);
+            }
+            if (!last) __syncthreads();
         }
-
-        // ---- store back in place (fire and forget) --------------------------------------------
-        {
-            amp *const *cptr = s_cptr_all + slot * n_chunks;
-            const unsigned char *tb = tiles_b + slot * tile_bytes;
-            for (uint32_t j = tid; j < tile_len; j += nthr)
-                *(cptr[j >> L] + (j & lmask)) = *reinterpret_cast<const amp *>(tb + 16u * swz(j));
-        }
-        __syncthreads();                 // this slot's tile buffer and metadata are free again
-        if (NB == 1) {
-            t_next = prepare(t_cur + gridDim.x, slot);
-            if (t_next < hdr.n_tiles) issue_load(slot);
-        } else {
-            slot ^= 1u;
-        }
+        mslot = mnext;
+        if (NB == 2) bslot ^= 1u;
         t_cur = t_next;
+        toff_cur = toff_next;
     }
 }
 
 constexpr size_t TILE_SMEM_MAX = 227u * 1024u;
 
 static size_t tile_smem_bytes(const TPassHdr &h, int nb) {
-    return (size_t)nb * ((size_t)16 << h.T) + (size_t)32 * h.n_ops + (size_t)32 * h.n_stages +
-           (size_t)nb * ((size_t)8 << (h.T - h.L)) + (size_t)nb * ((h.n_ops + 15u) & ~15u);
+    return (size_t)nb * ((size_t)16 << h.T) + (size_t)(MOP_BYTES + sizeof(MBase)) * h.n_ops + (size_t)32 * h.n_stages +
+           ((size_t)8 << (h.T - h.L)) + (size_t)META_SLOTS * ((h.n_ops + 15u) & ~15u);
 }
 
 typedef void (*tile_kernel_t)(const Segs, const TPassHdr, const TStage *, const MOp *, const MBase *, const amp *);
@@ -487,8 +765,9 @@ static tile_kernel_t pick_kernel(bool full) {
 int tile_kernel_setup() {
     bool ok = true;
     for (int full = 0; full < 2; ++full) {
-        const tile_kernel_t ks[3] = {pick_kernel<128, 3, 2>(full), pick_kernel<128, 3, 1>(full),
-                                     pick_kernel<256, 2, 1>(full)};
+        const tile_kernel_t ks[5] = {pick_kernel<128, 3, 2>(full), pick_kernel<128, 3, 1>(full),
+                                     pick_kernel<256, 2, 1>(full), pick_kernel<256, 1, 2>(full),
+                                     pick_kernel<128, 4, 1>(full)};
         for (tile_kernel_t k : ks)
             ok = ok && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)TILE_SMEM_MAX) == cudaSuccess;
@@ -496,7 +775,8 @@ int tile_kernel_setup() {
     return ok ? 0 : -1;
 }
 
-int g_tile_nbuf = 0;     // tuning knob (option "tile_nbuf"): 0 = auto, 1 / 2 = force for T <= 11
+int g_tile_stagger = 5000;   // tuning knob (option "tile_stagger"): start offset between the CTAs of an SM, cycles
+int g_tile_nbuf = 0;     // tuning knob (option "tile_nbuf"): 0 = auto, 1 / 2 = force the buffer count
 
 int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, const TStage *d_stages,
                      const MOp *d_ops, const MBase *d_bases, const amp *mat_table, int sm_count) {
@@ -507,19 +787,18 @@ int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, con
     tile_kernel_t kern;
     int threads, nb;
     if (hdr.T >= 12) {
-        kern = pick_kernel<256, 2, 1>(hdr.full != 0);
         threads = 256;
-        nb = 1;
+        nb = g_tile_nbuf == 2 ? 2 : 1;
+        if (nb == 2 && tile_smem_bytes(hdr, 2) > TILE_SMEM_MAX) nb = 1;
+        kern = nb == 2 ? pick_kernel<256, 1, 2>(hdr.full != 0) : pick_kernel<256, 2, 1>(hdr.full != 0);
     } else {
         threads = 1 << (hdr.T - TILE_R);
         if (threads < 32) threads = 32;
         if (threads > 128) threads = 128;
-        nb = 2;
-        kern = pick_kernel<128, 3, 2>(hdr.full != 0);
-        if (g_tile_nbuf == 1 || tile_smem_bytes(hdr, 2) > TILE_SMEM_MAX) {   // (very long pass programs)
-            nb = 1;
-            kern = pick_kernel<128, 3, 1>(hdr.full != 0);
-        }
+        nb = g_tile_nbuf == 2 ? 2 : 1;
+        if (nb == 2 && tile_smem_bytes(hdr, 2) > TILE_SMEM_MAX) nb = 1;
+        kern = nb == 2 ? pick_kernel<128, 3, 2>(hdr.full != 0)
+                       : g_tile_nbuf == 3 ? pick_kernel<128, 3, 1>(hdr.full != 0) : pick_kernel<128, 4, 1>(hdr.full != 0);
     }
     const size_t smem = tile_smem_bytes(hdr, nb);
     if (smem > TILE_SMEM_MAX) return -1;
@@ -528,7 +807,10 @@ int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, con
         per_sm = 1;
     uint64_t grid = (uint64_t)sm_count * per_sm;
     if (grid > hdr.n_tiles) grid = hdr.n_tiles;
-    kern<<<(unsigned)grid, threads, smem, st>>>(segs, hdr, d_stages, d_ops, d_bases, mat_table);
+    TPassHdr h2 = hdr;
+    h2.waves = (uint32_t)per_sm;
+    h2.stagger_cycles = grid > (uint64_t)sm_count ? (uint32_t)g_tile_stagger : 0u;
+    kern<<<(unsigned)grid, threads, smem, st>>>(segs, h2, d_stages, d_ops, d_bases, mat_table);
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 

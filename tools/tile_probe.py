@@ -34,12 +34,16 @@ def main():
     ap.add_argument("--chunk-bits", type=int, default=7)
     ap.add_argument("--nbuf", type=int, default=0)
     ap.add_argument("--no-mem", action="store_true")
+    ap.add_argument("--stagger", type=int, default=-1)
     ap.add_argument("--only-rx", type=int, default=0, help="run only the rx probe with this k (for ncu)")
+    ap.add_argument("--only-rot8", type=int, default=0, help="run only the rot8 probe with this k (for ncu)")
     args = ap.parse_args()
     n = args.qubits
     reg = QReg.new(n)
     hi = [n - 1, n - 2, n - 3, n - 4, n - 5, n - 6, n - 7, n - 8]
     reg.set_option("tile_nbuf", args.nbuf)
+    if args.stagger >= 0:
+        reg.set_option("tile_stagger", args.stagger)
     for tb in ((12, 11) if not args.no_mem else ()):
         for cb in (7, 4):
             if tb - cb > 8:
@@ -52,7 +56,14 @@ def main():
             print(f"mem   T={tb} L={cb} passes={passes} ms/pass={ms:.3f} GB/s={bpl / ms / 1e6:.0f}", flush=True)
     reg.set_option("tile_bits", args.tile_bits)
     reg.set_option("chunk_bits", args.chunk_bits)
-    print(f"--- T={args.tile_bits} L={args.chunk_bits} nbuf={args.nbuf}")
+    print(f"--- T={args.tile_bits} L={args.chunk_bits} nbuf={args.nbuf} stagger={args.stagger}")
+    if args.only_rot8:
+        circ = MultiOp()
+        for i in range(args.only_rot8):
+            circ *= (op.rx if i & 1 else op.ry)(0.1 + i, 1 << (4 * ((i // 8) % 3) + i % 4))
+        ms, passes, bpl = time_circ(reg, circ, reps=2)
+        print(f"rot8  k={args.only_rot8} passes={passes} ms/pass={ms:.3f}")
+        return
     if args.only_rx:
         circ = MultiOp()
         for i in range(args.only_rx):
@@ -66,6 +77,12 @@ def main():
             circ *= op.rx(0.1 + i, 1 << (i % args.tile_bits))
         ms, passes, bpl = time_circ(reg, circ)
         print(f"rx    k={k} passes={passes} ms/pass={ms:.3f} GB/s={bpl / ms / 1e6:.0f}", flush=True)
+    for k in (8, 16, 24, 32):
+        circ = MultiOp()
+        for i in range(k):     # 8 rotations per stage of 4 bits (the shape of configs[1])
+            circ *= (op.rx if i & 1 else op.ry)(0.1 + i, 1 << (4 * ((i // 8) % 3) + i % 4))
+        ms, passes, bpl = time_circ(reg, circ)
+        print(f"rot8  k={k} passes={passes} ms/pass={ms:.3f} GB/s={bpl / ms / 1e6:.0f}", flush=True)
     for k in (8, 32):
         circ = MultiOp()
         for i in range(k):
