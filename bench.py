@@ -203,6 +203,8 @@ def run_ours(args):
 
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)

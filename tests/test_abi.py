@@ -32,6 +32,15 @@ def test_python_binding_covers_header():
     assert sorted(_ffi.PROTOTYPES) == _declared_symbols()
 
 
+def test_rust_bindings_cover_header():
+    """rust/qvnt-b200-sys/src/lib.rs (uncompiled here: no Rust toolchain) declares every entry
+    point of the header, with the POD layouts the C side uses."""
+    rs = open(os.path.join(ROOT, "rust", "qvnt-b200-sys", "src", "lib.rs")).read()
+    declared = sorted(set(re.findall(r"pub fn (qvnt_[a-z0-9_]+)\(", rs)))
+    assert declared == _declared_symbols()
+    assert "pub matrix: [f64; 32]" in rs and "#[repr(C)]" in rs
+
+
 def test_op_layout():
     assert ctypes.sizeof(QvntOp) == 304
     assert QvntOp.a_mask.offset == 8 and QvntOp.ctrl.offset == 24
