@@ -147,3 +147,36 @@ def mixed_all_kinds(n: int, layers: int, seed: int = 7) -> MultiOp:
                 g = g.c(c)
         circ *= g
     return circ
+
+
+def qasm_config5(n: int, layers: int, seed: int = 0x51415335) -> str:
+    """configs[4]: OpenQASM 2.0 text, generated deterministically --
+    `h q;` then layers of multi-controlled Toffolis (ccx / cccx chains reaching across the
+    register, so the controls land on sharded qubits), rzz and i_swap pairs, a final
+    `measure q -> c;`.  Gate names as lowered by qasm/int/gates.rs:111,115."""
+    rng = SplitMix64(seed)
+    out = ["OPENQASM 2.0;", f"qreg q[{n}];", f"creg c[{n}];", "h q;"]
+
+    def pick(k):
+        s = []
+        while len(s) < k:
+            v = rng.next() % n
+            if v not in s:
+                s.append(v)
+        return s
+    for layer in range(layers):
+        for _ in range(max(1, n // 6)):
+            a, b, c = pick(3)
+            out.append(f"ccx q[{a}],q[{b}],q[{c}];")
+        a, b, c, d = pick(4)
+        out.append(f"cccx q[{a}],q[{b}],q[{c}],q[{d}];")
+        for _ in range(max(1, n // 4)):
+            a, b = pick(2)
+            out.append(f"rzz({rng.angle():.17g}) q[{a}],q[{b}];")
+        for _ in range(max(1, n // 6)):
+            a, b = pick(2)
+            out.append(f"i_swap q[{a}],q[{b}];")
+        if layer % 2 == 1:
+            out.append(f"rx(pi/{2 + layer % 5}) q[{pick(1)[0]}];")
+    out.append("measure q -> c;")
+    return "\n".join(out) + "\n"
