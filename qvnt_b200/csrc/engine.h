@@ -61,7 +61,8 @@ enum TForm : uint32_t {
     TF_PAIR2X = 2,  // rxx/ryy: partner differs in slots ra and rb
     TF_ODD2 = 3,    // swap family: odd-parity pair {slot ra set, slot rb set}
     TF_QUAD = 4,    // h2/u2: a = slot ra, b = slot rb
-    TF_LAZYX = 5    // x between threads: no register slot
+    TF_LAZYX = 5,   // x between threads: no register slot
+    TF_GROUP = 6    // header of a merged diagonal run (not an op of its own)
 };
 
 // Dispatch codes of the stage interpreter (tile.cu).  Two-bit ops sit on the slot pairs
@@ -96,8 +97,11 @@ enum FCode : uint8_t {
                   //         reference's own operation order, h1.rs:16-22; h2 halves use c0 = 1 and 0.5)
     FC_LX = 22,   // lazy x: target and controls on thread / outer bits (a_thr = target's thread bit,
                   //         a_reg = its tile-local position); no register slot involved
-    FC_COUNT = 23,
-    FC_ALL = 23   // added to the code when no control sits in a register slot (okmask == 0xFFFF)
+    FC_DM = 23,   // header of a run of a_reg (in MOp::a_reg) diagonal ops that share their controls and
+                  //         have no target bit in a register slot: their factors are multiplied into ONE
+                  //         complex number per thread, applied to the 16 amplitudes once
+    FC_COUNT = 24,
+    FC_ALL = 24   // added to the code when no control sits in a register slot (okmask == 0xFFFF)
 };
 constexpr uint8_t MOP_SKIP0 = 0x02;   // MOp::dagger bit 1 (fast diagonal forms): f0 == 1, even parity untouched
 

@@ -532,7 +532,7 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
         std::vector<StageSel> s2;
         while (!c2.empty()) {
             Slots sl;
-            const size_t room = (size_t)TILE_MAX_OPS - (plan.mops.size() - cur.hdr.op_begin);
+            const size_t room = ((size_t)TILE_MAX_OPS - (plan.mops.size() - cur.hdr.op_begin)) * 3 / 4;   // (+ run headers)
             stage_select(pl, c2, set, room, s2, r2, sl, pass_fast && !getenv("QVNT_NO_LAZYX"));
             if (s2.empty() || plan.stages.size() - cur.hdr.stage_begin >= (size_t)TILE_MAX_STAGES) {
                 if (plan.mops.size() == cur.hdr.op_begin) {
@@ -625,7 +625,7 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                             split(p.d.a, treg, tthr, tbase);
                             m.code = (uint8_t)FC_LX;
                             m.a_thr = tthr;
-                            m.a_reg = (uint16_t)lpos_of[ctz64(p.d.a)];
+                            m.a_reg = (uint16_t)(lpos_of[ctz64(p.d.a)] | (ctz64(p.d.a) << 8));
                             mi.form = TF_LAZYX;
                             mi.ra = mi.rb = 0;
                         } else {
@@ -703,6 +703,54 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                 plan.bases.push_back(b);
                 plan.minfo.push_back(mi);
                 cur.ops.push_back(ss.idx);
+            }
+            // ---- merge runs of diagonal ops (fast passes) ----
+            // Consecutive diagonal ops with no target bit in a register slot and identical controls
+            // multiply every amplitude of a thread by thread-wide factors: a header op (FC_DM) makes
+            // the kernel fold the run into ONE complex factor per thread (4 FP64 instructions per
+            // constituent instead of 64) -- qft's chains of controlled rz behind every h.
+            if (pass_fast) {
+                const size_t b0 = st.op_begin;
+                std::vector<MOp> mo(plan.mops.begin() + b0, plan.mops.end());
+                std::vector<MBase> ba(plan.bases.begin() + b0, plan.bases.end());
+                std::vector<MInfo> mf(plan.minfo.begin() + b0, plan.minfo.end());
+                plan.mops.resize(b0);
+                plan.bases.resize(b0);
+                plan.minfo.resize(b0);
+                auto is_du = [&](size_t k) {
+                    return mo[k].code == (uint8_t)FC_DU || mo[k].code == (uint8_t)(FC_ALL + FC_DU);
+                };
+                for (size_t k = 0; k < mo.size();) {
+                    size_t e = k;
+                    if (is_du(k)) {
+                        e = k + 1;
+                        while (e < mo.size() && is_du(e) && mo[e].okmask == mo[k].okmask &&
+                               mo[e].ctrl_thr == mo[k].ctrl_thr && ba[e].ctrl_base == ba[k].ctrl_base && e - k < 4096)
+                            ++e;
+                    }
+                    if (e - k >= 3) {
+                        MOp hd;
+                        MBase hb;
+                        memset(&hd, 0, sizeof(hd));
+                        memset(&hb, 0, sizeof(hb));
+                        hd.code = (uint8_t)FC_DM;
+                        hd.okmask = mo[k].okmask;
+                        hd.ctrl_thr = mo[k].ctrl_thr;
+                        hd.a_reg = (uint16_t)(e - k);
+                        hb.ctrl_base = ba[k].ctrl_base;
+                        plan.mops.push_back(hd);
+                        plan.bases.push_back(hb);
+                        plan.minfo.push_back({mf[k].src, TF_GROUP, 0, 0});
+                    } else if (e == k) {
+                        e = k + 1;
+                    }
+                    for (size_t q = k; q < e; ++q) {
+                        plan.mops.push_back(mo[q]);
+                        plan.bases.push_back(ba[q]);
+                        plan.minfo.push_back(mf[q]);
+                    }
+                    k = e;
+                }
             }
             st.op_end = (uint32_t)plan.mops.size();
             plan.stages.push_back(st);

@@ -259,25 +259,35 @@ struct StageCtx {
     uint32_t c[TR];     // swizzled byte offsets of the 4 register-slot bits
     uint32_t jl;        // tile-local index of slot pattern 0
     uint32_t mine_o;    // its swizzled byte offset
+    unsigned long long goff;   // last stage, local tiles: byte offset of jl inside the tile's span of the shard
 };
 
-__device__ __forceinline__ StageCtx stage_ctx(const uint32_t stage_s, const uint32_t n_t, const uint32_t grp) {
+// Per-(stage, thread) constants are computed ONCE per kernel (every tile of the pass runs the same
+// stages) and kept in shared memory: word = (16 * swz(jl)) << 16 | jl.
+__device__ __forceinline__ uint32_t stage_jl(const uint32_t stage_s, const uint32_t n_t, const uint32_t grp) {
     uint32_t sw[8];      // the TStage: op_begin, op_end, r_lpos[4], t_lpos[16], pad
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
                  : "=r"(sw[0]), "=r"(sw[1]), "=r"(sw[2]), "=r"(sw[3]) : "r"(stage_s) : "memory");
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
                  : "=r"(sw[4]), "=r"(sw[5]), "=r"(sw[6]), "=r"(sw[7]) : "r"(stage_s + 16u) : "memory");
-    StageCtx x;
-    x.r_lpos = sw[2];
-#pragma unroll
-    for (int j = 0; j < TR; ++j) x.c[j] = 16u * swz(1u << ((sw[2] >> (8 * j)) & 0xFFu));
     uint32_t jl = 0;
 #pragma unroll
     for (uint32_t k = 0; k < 16; ++k) {
         if (k < n_t) jl |= ((grp >> k) & 1u) << ((sw[3 + (k >> 2)] >> (8 * (k & 3))) & 0xFFu);
     }
-    x.jl = jl;
-    x.mine_o = 16u * swz(jl);
+    return jl;
+}
+
+__device__ __forceinline__ StageCtx stage_ctx(const uint32_t stage_s, const uint32_t jltab_s, const uint32_t ctab_s) {
+    StageCtx x;
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(x.r_lpos) : "r"(stage_s + 8u) : "memory");
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(x.c[0]), "=r"(x.c[1]), "=r"(x.c[2]), "=r"(x.c[3]) : "r"(ctab_s) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(w) : "r"(jltab_s) : "memory");
+    x.jl = w & 0xFFFFu;
+    x.mine_o = w >> 16;
+    x.goff = 0;
     return x;
 }
 
@@ -331,6 +341,29 @@ __device__ __forceinline__ void stage_store_global(const uint32_t ptr0_s, const 
         unsigned long long base;
         asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(base) : "r"(ch) : "memory");
         *reinterpret_cast<amp *>(base + off0 + off) = v[K];
+    }
+}
+
+// Same, for tiles that lie entirely in this GPU's shard: the address is affine in the index bits,
+// address(K) = base + goff(thread) + sum of the byte offsets of K's register-slot bits -- no table.
+__device__ __forceinline__ void stage_store_global_local(const unsigned long long base, const uint32_t gpos_s,
+                                                         const StageCtx &x, const amp (&v)[NV]) {
+    unsigned long long g[TR];
+#pragma unroll
+    for (int j = 0; j < TR; ++j) {
+        uint32_t gp;
+        asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(gp) : "r"(gpos_s + ((x.r_lpos >> (8 * j)) & 0xFFu)) : "memory");
+        g[j] = 16ull << gp;
+    }
+    const unsigned long long a0 = base + x.goff;
+#pragma unroll
+    for (int K = 0; K < NV; ++K) {
+        unsigned long long a = a0;
+        if (K & 1) a += g[0];
+        if (K & 2) a += g[1];
+        if (K & 4) a += g[2];
+        if (K & 8) a += g[3];
+        *reinterpret_cast<amp *>(a) = v[K];
     }
 }
 
@@ -567,11 +600,41 @@ __device__ __forceinline__ void stage_ops_fast(const uint32_t ops_s, const uint3
                      : "=r"(m.w0), "=r"(m.ctrl_thr), "=r"(m.a_thr), "=r"(m.a_reg)
                      : "r"(op_a)
                      : "memory");
-        if (!(fl & 0x80u) || (~vgrp & m.ctrl_thr)) continue;
+        if (!(fl & 0x80u) || (~vgrp & m.ctrl_thr)) {
+            if ((m.w0 & 0xFFu) == (uint32_t)FC_DM) o += m.a_reg & 0xFFFFu;     // the whole run shares the controls
+            continue;
+        }
+        if ((m.w0 & 0xFFu) == (uint32_t)FC_DM) {
+            // merged diagonal run: acc = product of the constituents' factors for this thread
+            const uint32_t cnt = m.a_reg & 0xFFFFu;
+            double ar = 1.0, ai = 0.0;
+            for (uint32_t k = 1; k <= cnt; ++k) {
+                const uint32_t a2 = op_a + MOP_BYTES * k;
+                uint32_t fl2, w2, athr2;
+                asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(fl2) : "r"(flags_s + o + k) : "memory");
+                asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(w2) : "r"(a2) : "memory");
+                asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(athr2) : "r"(a2 + 8u) : "memory");
+                const uint32_t par = (__popc(vgrp & athr2) + fl2) & 1u;
+                if (!par && (w2 & ((uint32_t)MOP_SKIP0 << 8))) continue;
+                double fr, fi;
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(fr), "=d"(fi) : "r"(a2 + 16u + 16u * par) : "memory");
+                const double t = ar * fr - ai * fi;
+                ai = ar * fi + ai * fr;
+                ar = t;
+            }
+            const uint32_t ok = m.w0 >> 16;
+            const double nai = -ai;
+            QV_FOR_K {
+                if ((ok >> K) & 1u) f_cmul(v[K], ar, ai, nai);
+            }
+            o += cnt;
+            continue;
+        }
         if ((m.w0 & 0xFFu) == (uint32_t)FC_LX) {
             vgrp ^= m.a_thr;
             x.jl ^= 1u << (m.a_reg & 0xFFu);
             x.mine_o ^= 16u * swz(1u << (m.a_reg & 0xFFu));
+            x.goff ^= 16ull << (m.a_reg >> 8);           // (a_reg high byte: the bit's position in the shard)
             continue;
         }
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(m.c0), "=d"(m.c1) : "r"(op_a + 16u) : "memory");
@@ -612,7 +675,11 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     TStage *s_stages = reinterpret_cast<TStage *>(s_ops + n_ops);                  // 32 * n_stages
     MBase *s_bases = reinterpret_cast<MBase *>(s_stages + n_stages);               // 16 * n_ops
     unsigned long long *s_ptr0 = reinterpret_cast<unsigned long long *>(s_bases + n_ops);   // 8 * n_chunks
-    uint8_t *s_flags_all = reinterpret_cast<uint8_t *>(s_ptr0 + n_chunks);         // 3 * flags_stride
+    unsigned long long *s_goff = s_ptr0 + ((n_chunks + 1u) & ~1u);                 // 8 * nthr (last stage)
+    uint32_t *s_ctab = reinterpret_cast<uint32_t *>(s_goff + nthr);                // 16 * n_stages
+    uint32_t *s_jltab = s_ctab + 4u * n_stages;                                    // 4 * nthr * n_stages
+    uint8_t *s_gpos = reinterpret_cast<uint8_t *>(s_jltab + nthr * n_stages);      // 16
+    uint8_t *s_flags_all = s_gpos + 16;                                            // 3 * flags_stride
 
     const uint32_t shard_shift = segs.shift;
     const uint64_t shard_mask = (1ull << shard_shift) - 1ull;
@@ -638,7 +705,26 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
         }
     }
     const uint32_t n_t = T - TR;                     // thread bits per stage
+    if (tid < 16u) s_gpos[tid] = hdr.gpos[tid];
+    __syncthreads();                                 // the stage descriptors are in shared memory
+    // per-(stage, thread) and per-stage constants, once per kernel
+    for (uint32_t st = 0; st < n_stages; ++st) {
+        const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(s_stages + st);
+        const uint32_t jl = stage_jl(stage_s, n_t, tid);
+        s_jltab[st * nthr + tid] = ((16u * swz(jl)) << 16) | jl;
+        if (tid < (uint32_t)TR) s_ctab[4u * st + tid] = 16u * swz(1u << s_stages[st].r_lpos[tid]);
+        if (st + 1 == n_stages) {
+            unsigned long long go = 0;
+            for (uint32_t l = 0; l < T; ++l)
+                if ((jl >> l) & 1u) go += 16ull << hdr.gpos[l];
+            s_goff[tid] = go;
+        }
+    }
     const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(tiles_b);
+    const uint32_t jltab_s = (uint32_t)__cvta_generic_to_shared(s_jltab);
+    const uint32_t ctab_s = (uint32_t)__cvta_generic_to_shared(s_ctab);
+    const uint32_t gpos_s = (uint32_t)__cvta_generic_to_shared(s_gpos);
+    const unsigned long long shard_base = (unsigned long long)(uintptr_t)segs.seg[segs.rank];
     const uint32_t ops_s = (uint32_t)__cvta_generic_to_shared(s_ops);
     const uint32_t stages_s = (uint32_t)__cvta_generic_to_shared(s_stages);
     const uint32_t flags_all_s = (uint32_t)__cvta_generic_to_shared(s_flags_all);
@@ -726,7 +812,8 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
             amp v[NV];
             StageCtx x;
             if (active) {
-                x = stage_ctx(stages_s + 32u * s, n_t, tid);
+                x = stage_ctx(stages_s + 32u * s, jltab_s + 4u * (s * nthr + tid), ctab_s + 16u * s);
+                if (last) x.goff = s_goff[tid];
                 stage_load(tile_s, x, v);
             }
             if (last && NB == 1) {
@@ -736,8 +823,9 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
             if (active) {
                 if (FULL) stage_ops_full(ops_s, flags_s, ob, oe, tid, mats, v);
                 else stage_ops_fast(ops_s, flags_s, ob, oe, tid, x, v);
-                if (last) stage_store_global(ptr0_s, L, toff_cur, x, v);
-                else stage_store_smem(tile_s, x, v);
+                if (!last) stage_store_smem(tile_s, x, v);
+                else if (hdr.touches_peer) stage_store_global(ptr0_s, L, toff_cur, x, v);
+                else stage_store_global_local(shard_base + toff_cur, gpos_s, x, v);
             }
             if (!last) __syncthreads();
         }
@@ -750,9 +838,10 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
 
 constexpr size_t TILE_SMEM_MAX = 227u * 1024u;
 
-static size_t tile_smem_bytes(const TPassHdr &h, int nb) {
+static size_t tile_smem_bytes(const TPassHdr &h, int nb, int threads = 256) {
     return (size_t)nb * ((size_t)16 << h.T) + (size_t)(MOP_BYTES + sizeof(MBase)) * h.n_ops + (size_t)32 * h.n_stages +
-           ((size_t)8 << (h.T - h.L)) + (size_t)META_SLOTS * ((h.n_ops + 15u) & ~15u);
+           ((size_t)8 << (h.T - h.L)) + 8 + (size_t)META_SLOTS * ((h.n_ops + 15u) & ~15u) +
+           (size_t)8 * threads + (size_t)16 * h.n_stages + (size_t)4 * threads * h.n_stages + 16;
 }
 
 typedef void (*tile_kernel_t)(const Segs, const TPassHdr, const TStage *, const MOp *, const MBase *, const amp *);
@@ -765,9 +854,9 @@ static tile_kernel_t pick_kernel(bool full) {
 int tile_kernel_setup() {
     bool ok = true;
     for (int full = 0; full < 2; ++full) {
-        const tile_kernel_t ks[5] = {pick_kernel<128, 3, 2>(full), pick_kernel<128, 3, 1>(full),
+        const tile_kernel_t ks[6] = {pick_kernel<128, 3, 2>(full), pick_kernel<128, 3, 1>(full),
                                      pick_kernel<256, 2, 1>(full), pick_kernel<256, 1, 2>(full),
-                                     pick_kernel<128, 4, 1>(full)};
+                                     pick_kernel<128, 4, 1>(full), pick_kernel<128, 5, 1>(full)};
         for (tile_kernel_t k : ks)
             ok = ok && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)TILE_SMEM_MAX) == cudaSuccess;
@@ -798,9 +887,10 @@ int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, con
         nb = g_tile_nbuf == 2 ? 2 : 1;
         if (nb == 2 && tile_smem_bytes(hdr, 2) > TILE_SMEM_MAX) nb = 1;
         kern = nb == 2 ? pick_kernel<128, 3, 2>(hdr.full != 0)
-                       : g_tile_nbuf == 3 ? pick_kernel<128, 3, 1>(hdr.full != 0) : pick_kernel<128, 4, 1>(hdr.full != 0);
+                       : g_tile_nbuf == 3 ? pick_kernel<128, 3, 1>(hdr.full != 0)
+                       : g_tile_nbuf == 5 ? pick_kernel<128, 5, 1>(hdr.full != 0) : pick_kernel<128, 4, 1>(hdr.full != 0);
     }
-    const size_t smem = tile_smem_bytes(hdr, nb);
+    const size_t smem = tile_smem_bytes(hdr, nb, threads);
     if (smem > TILE_SMEM_MAX) return -1;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1)

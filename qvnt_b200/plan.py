@@ -79,6 +79,8 @@ def describe(q_num: int, circ, rank: int = 0, world: int = 1, peers: bool = Fals
             passes[-1].stages.append(PlanStage(r_lpos=_ints(kv["r"]), t_lpos=_ints(kv["t"])))
         elif tok[0] == "op":
             o = PlanOp(**{k: int(v) for k, v in kv.items()})
+            if o.form == 6:          # header of a merged diagonal run: not an op of its own
+                continue
             if passes[-1].direct:
                 passes[-1].op = o
             else:
