@@ -58,6 +58,17 @@ def build_workload(args):
     return n, circ, name
 
 
+def measured_traffic(kernel, n_local):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed `ncu --set full` capture (profiles/traffic.json: bytes moved per amplitude)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        per_amp = json.load(open(p))[kernel]["dram_bytes_per_amplitude"]
+        return per_amp * float(1 << n_local)
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -303,7 +314,10 @@ def run_ours(args):
     if sp["launches"][dom]:
         achieved = sp["alg_bytes"][dom] / (sp["ms"][dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": CLASS_NAMES[dom], "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": measured_traffic(CLASS_NAMES[dom], n - (world.bit_length() - 1)),
+                    "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel, per amplitude)",
+                    "peak_source": peak_src,
                     "launches_per_step": int(sp["launches"][dom]),
                     "avg_launch_ms": sp["ms"][dom] / sp["launches"][dom],
                     "alg_bytes_per_launch": sp["alg_bytes"][dom] / sp["launches"][dom],
