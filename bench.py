@@ -191,7 +191,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tt / len(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": {"workload": name, "qubits": n, "single_ops": len(ops),
-                                        "ops_per_step": k},
+                                        "state_bytes": 16 << n, "ops_per_step": k},
         "cpu_baseline": {"value": v, "unit": "gates/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "amplitude_gbs": v * 32 * (1 << n) / 1e9,
