@@ -618,6 +618,7 @@ int qvnt_reg_set_option(qvnt_reg_t *r, const char *key, int64_t value) {
     } else if (!strcmp(key, "tma")) r->opt_tma = value != 0;
     else if (!strcmp(key, "tile_nbuf")) g_tile_nbuf = (int)value;
     else if (!strcmp(key, "tile_stagger")) g_tile_stagger = (int)value;
+    else if (!strcmp(key, "tile_sysload")) g_tile_sysload = (int)value;
     else if (!strcmp(key, "profile")) {
         int rc = use(r);
         if (rc) return rc;

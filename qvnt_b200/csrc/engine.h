@@ -128,7 +128,8 @@ struct TStage {       // 32 bytes
     uint32_t op_begin, op_end;   // range in the uploaded MOp array
     uint8_t r_lpos[4];           // register slot j -> tile-local bit position
     uint8_t t_lpos[16];          // thread bit k    -> tile-local bit position (T - TILE_R entries)
-    uint32_t _pad;
+    uint32_t sync_after_load;    // the stage holds a lazy x: threads store to OTHER threads' shared-memory
+                                 // slots, so every thread must have loaded before any thread stores
 };
 static_assert(sizeof(TStage) == 32, "TStage layout");
 
@@ -148,6 +149,7 @@ struct TPassHdr {
     uint32_t touches_peer;       // some tile bit is a rank bit
     uint32_t full;               // some op needs the full interpreter (u1/u2, two-bit pair ops, multi-bit masks)
     uint32_t waves, stagger_cycles;   // filled by launch_tile_pass: CTAs per SM, start offset between them
+    uint32_t sysload, _pad2;
     uint16_t stage_end[TILE_MAX_STAGES];   // ops of stage s: [stage_end[s-1], stage_end[s]) relative to op_begin
     Fixed fx;                    // the same enumeration bit by bit (host side: describe / tests)
 };
@@ -157,6 +159,7 @@ int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, con
 int tile_kernel_setup();
 extern int g_tile_nbuf;
 extern int g_tile_stagger;
+extern int g_tile_sysload;
 
 // ---- measurement / utility kernels (measure.cu) -----------------------------
 constexpr int REDUCE_BLOCKS_MAX = 4096;

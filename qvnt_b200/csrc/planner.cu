@@ -624,6 +624,7 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                             uint64_t tbase;
                             split(p.d.a, treg, tthr, tbase);
                             m.code = (uint8_t)FC_LX;
+                            st.sync_after_load = 1;
                             m.a_thr = tthr;
                             m.a_reg = (uint16_t)(lpos_of[ctz64(p.d.a)] | (ctz64(p.d.a) << 8));
                             mi.form = TF_LAZYX;

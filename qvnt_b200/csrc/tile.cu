@@ -565,13 +565,17 @@ __device__ __forceinline__ void apply_fop(const FDec &m, const uint32_t fl, cons
     uint32_t code = m.w0 & 0xFFu;
     asm volatile("" : "+r"(code));
     switch (code) {
+#ifndef QV_EXP_SMALL
     QV_F4(farm_pr, false, FC_PR, v, m, ok)
     QV_F4(farm_px, false, FC_PX, v, m, ok)
+#endif
     QV_F4(farm_sw, false, FC_SW, v, ok)
+#ifndef QV_EXP_SMALL
     case FC_DU: farm_du<false>(v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u); break;
     QV_F4(farm_ds, false, FC_DS, v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u)
     case FC_DG: farm_dg(v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u); break;
     QV_F4(farm_pa, false, FC_PA, v, m, ok)
+#endif
     QV_F4(farm_pr, true, FC_ALL + FC_PR, v, m, ok)
     QV_F4(farm_px, true, FC_ALL + FC_PX, v, m, ok)
     QV_F4(farm_sw, true, FC_ALL + FC_SW, v, ok)
@@ -767,6 +771,17 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     const bool regular = (nthr & lmask) == 0u && (tile_len % nthr) == 0u;
     auto issue_load = [&](const unsigned long long toff, uint32_t bslot) {
         const uint32_t tb_s = tiles_s + bslot * tile_bytes;
+        if (hdr.sysload) {
+            // peer tiles: system-scope loads (never served from a requester-side cache)
+            for (uint32_t j = tid; j < tile_len; j += nthr) {
+                const unsigned long long p = s_ptr0[j >> L] + toff + (unsigned long long)(j & lmask) * 16ull;
+                double a, b;
+                asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];\n" : "=d"(a), "=d"(b) : "l"(p) : "memory");
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(tb_s + 16u * swz(j)), "d"(a), "d"(b) : "memory");
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+            return;
+        }
         if (regular) {
             const unsigned long long mine = toff + (unsigned long long)(tid & lmask) * 16ull;
             const uint32_t cstep = (nthr >> L) * 8u;
@@ -819,6 +834,10 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
             if (last && NB == 1) {
                 __syncthreads();                       // every thread holds its amplitudes: the buffer is free
                 if (has_next) issue_load(toff_next, bslot);
+            } else if (!last && s_stages[s].sync_after_load) {
+                // a lazy x makes threads store into each other's slots of the tile buffer: nobody
+                // may store before everybody has loaded
+                __syncthreads();
             }
             if (active) {
                 if (FULL) stage_ops_full(ops_s, flags_s, ob, oe, tid, mats, v);
@@ -834,6 +853,10 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
         t_cur = t_next;
         toff_cur = toff_next;
     }
+    // Stores into a peer's HBM must be performed at SYSTEM scope before the barrier kernel that
+    // follows signals the peers: the barrier's own fence is executed by other threads and does not
+    // cover them.
+    if (hdr.touches_peer) __threadfence_system();
 }
 
 constexpr size_t TILE_SMEM_MAX = 227u * 1024u;
@@ -864,7 +887,8 @@ int tile_kernel_setup() {
     return ok ? 0 : -1;
 }
 
-int g_tile_stagger = 5000;   // tuning knob (option "tile_stagger"): start offset between the CTAs of an SM, cycles
+int g_tile_stagger = 0;      // experiment knob (option "tile_stagger"): start offset between the CTAs of an SM, cycles (no measurable effect)
+int g_tile_sysload = 0;    // debug/safety knob (option "tile_sysload"): system-scope loads for peer tiles
 int g_tile_nbuf = 0;     // tuning knob (option "tile_nbuf"): 0 = auto, 1 / 2 = force the buffer count
 
 int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, const TStage *d_stages,
@@ -900,6 +924,7 @@ int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, con
     TPassHdr h2 = hdr;
     h2.waves = (uint32_t)per_sm;
     h2.stagger_cycles = grid > (uint64_t)sm_count ? (uint32_t)g_tile_stagger : 0u;
+    h2.sysload = (g_tile_sysload && hdr.touches_peer) ? 1u : 0u;
     kern<<<(unsigned)grid, threads, smem, st>>>(segs, h2, d_stages, d_ops, d_bases, mat_table);
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }

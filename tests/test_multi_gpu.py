@@ -151,3 +151,19 @@ def test_p_invariance():
     for world in (2, 4):
         got, _, _ = run_sharded(n, world, 0, circ)
         assert np.abs(got - want).max() <= AMP_TOL
+
+
+def test_sharded_lazy_x_large_tiles_regression():
+    """Regression: a lazy x makes threads store into each other's slots of the tile buffer; without
+    a barrier between a stage's loads and stores a fast warp could overwrite amplitudes a slow warp
+    had not loaded yet.  Only showed with >= 2^26-amplitude shards and two kernels sharing the GPU
+    (found by the norm check of tools/run_sharded.py at 34 qubits on 8 GPUs)."""
+    n = 27
+    circ = workloads.random_layered(n, 20)
+    ref = QReg.new(n)
+    ref.apply(circ)
+    want = ref.amplitudes()
+    ref.close()
+    got, _, _ = run_sharded(n, 2, 0, circ)
+    assert abs(float(np.vdot(got, got).real) - 1.0) < 1e-12
+    assert np.abs(got - want).max() <= AMP_TOL
