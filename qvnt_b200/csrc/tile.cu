@@ -20,28 +20,36 @@
 // The swizzle is GF(2)-linear, so a thread's 16 slot addresses are one base XOR 16
 // stage-uniform constants.
 //
-// The stage interpreter.  A stage keeps TILE_R = 4 tile bits in "register slots": every
-// thread holds the 16 amplitudes that differ in those bits.  An op is a 32-byte MOp in
-// shared memory whose `code` selects a fully unrolled body (kind x slot); everything
-// that depends on the amplitude index was split by the planner into
-//   - register-slot part: compile-time per slot (signs of ry/h1/y/ryy, rows of u1/u2) or a
-//     16-bit `okmask` (controls sitting in register slots),
+// Stages.  A stage keeps TILE_R = 4 tile bits in "register slots": every thread holds the 16
+// amplitudes that differ in those bits, runs all of the stage's ops on them and only then touches
+// shared memory again.  The last stage of a pass stores its registers straight to HBM, so the tile
+// buffer is free as soon as that stage has read it and the next tile's cp.async loads are issued
+// there.  An op is a 48-byte MOp in shared memory whose `code` selects a fully unrolled arm;
+// everything that depends on the amplitude index was split by the planner into
+//   - register-slot part: compile-time per arm, or a 16-bit `okmask` (controls in register slots),
 //   - thread part: one AND/compare on the thread's group number per op,
 //   - tile part: one flag byte per op per tile (controls / diagonal-mask bits outside the
 //     tile), computed once per tile.
 // Tiles none of whose ops is active (multi-controlled gates) are skipped without being read.
 //
-// Arithmetic: every gate uses the reference's formula (gates.cuh) with FMA contraction
-// off, on the same operands as the reference's gather form; only the ORDER of commuting
-// gates may differ from the op list (planner.cu).
+// Two interpreters share the plumbing: the FULL one carries every kind with the reference's
+// formulas (gates.cuh); the FAST one (passes made of x, y, rx, ry, h1, z/s/t on one bit, rz, rzz)
+// runs coefficient-driven arms written as in-place inline PTX -- see "FAST stage interpreter".
+//
+// Arithmetic: this file is compiled with FMA contraction ON (csrc/Makefile) and the planner may
+// exchange COMMUTING ops, so the fused path is parity-checked at 1e-10, not bit-exact; the direct
+// sweeps (direct.cu, -fmad=false) are the bit-exact path.
+//
+// Hazards the barriers cover: (1) between stages (threads exchange amplitudes through the tile
+// buffer); (2) before the next tile's loads overwrite the buffer (after the last stage's loads);
+// (3) between a stage's loads and stores when the stage holds a lazy x, because threads then store
+// into EACH OTHER's slots (TStage::sync_after_load); (4) across GPUs, dist_barrier() kernels
+// around every pass that touches a peer shard, plus a system fence after the peer stores.
 #include "engine.h"
 #include "gates.cuh"
 
 namespace qv {
 
-#ifndef QV_OP_PREFETCH
-#define QV_OP_PREFETCH 0
-#endif
 constexpr int NV = TILE_NV;
 constexpr int TR = TILE_R;
 
@@ -52,9 +60,6 @@ __device__ __forceinline__ uint32_t swz(uint32_t j) {
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
 // ---- op bodies: templated on kind and register slot(s), fully unrolled over the 16 slots -----
