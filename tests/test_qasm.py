@@ -147,3 +147,24 @@ def test_config5_twin_device_vs_oracle(oracle, n, layers):
     assert dev.get_class().get() == ref.get_class().get()
     assert np.abs(dev.q_reg.amplitudes() - ref.q_reg.amplitudes()).max() <= 1e-10
     assert np.abs(dev.get_probabilities() - ref.get_probabilities()).max() <= 1e-12
+
+
+# ---- the reference's own smoke programs (qasm/mod.rs:15-39) ----------------------------------------
+_EXAMPLES = "/root/reference/src/qasm/examples/source"
+_NAMES = ["adder", "bigadder", "Deutsch_Algorithm", "inverseqft1", "inverseqft2", "ipea_3_pi_8", "qe_qft_3",
+          "qe_qft_4", "qe_qft_5", "qec", "qft", "qpt", "rb", "teleport", "teleportv2", "W-state", "W3test"]
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(_EXAMPLES),
+                    reason="reference checkout not present (it never is on the GPU box)")
+@pytest.mark.parametrize("name", _NAMES)
+def test_reference_example_programs_run(oracle, name):
+    """`run_qasm` of the reference: build the program, Sym::reset(); Sym::finish() -- read from the
+    reference checkout where it lies (never copied); here additionally: probabilities sum to 1."""
+    src = open(f"{_EXAMPLES}/{name}.qasm").read()
+    prog = Int(src)
+    sym = Sym(prog, reg_factory=lambda k: oracle.OracleReg.new(k))
+    sym.reset()
+    sym.finish(us=[0.37] * 64)
+    assert abs(float(sym.get_probabilities().sum()) - 1.0) < 1e-9
+    assert sym.get_class().get() >> max(1, len(prog.c_reg)) == 0
