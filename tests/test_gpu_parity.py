@@ -292,3 +292,25 @@ def test_fullsize_config2_fused_equals_unfused():
     for off in rng.integers(0, (1 << n) - (1 << 16), 6):
         off = int(off)
         assert np.abs(a.amplitudes(off, 1 << 16) - b.amplitudes(off, 1 << 16)).max() <= AMP_TOL
+
+
+def test_polar_clone_and_sample_all(oracle):
+    """get_polar (quant.rs:417-431: Complex::to_polar = (norm, arg)), Clone (:102) and the shape
+    of sample_all (quant.rs:513-594 is only pinned by `histogram`, :714-725: length and sum)."""
+    n = 10
+    g, o = both(oracle, n, seed=42)
+    g.apply(workloads.mixed_all_kinds(n, 30, seed=5))
+    o.apply(workloads.mixed_all_kinds(n, 30, seed=5))
+    a = o.amplitudes()
+    pol = g.get_polar()
+    assert np.abs(pol[:, 0] - np.abs(a)).max() <= 1e-12
+    big = np.abs(a) > 1e-6
+    d = np.angle(np.exp(1j * (pol[big, 1] - np.angle(a[big]))))
+    assert np.abs(d).max() <= 1e-9
+    c = g.clone()
+    g.apply(op.x(1))                                  # the clone owns its own buffer
+    assert np.abs(c.amplitudes() - a).max() <= AMP_TOL
+    hist = c.sample_all(2048, rng=np.random.default_rng(1))
+    assert len(hist) == 1 << n and sum(hist) == 2048
+    p = c.get_probabilities()
+    assert np.abs(np.array(hist) / 2048.0 - p).max() < 0.05
