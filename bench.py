@@ -274,6 +274,7 @@ def run_ours(args):
         ms = float(t.item())
     launches = int(sum(st["launches"]))
     value = n_ops * args.steps / (ms * 1e-3)
+    timed_alg_gbs = [b / (ms * 1e-3) / 1e9 for b in st["alg_bytes"]]      # per class, over the timed region
 
     # ---- e2e: public API with host buffers, wall clock, copies inside --------------------------
     reg.stats_reset()
@@ -315,6 +316,9 @@ def run_ours(args):
         achieved = sp["alg_bytes"][dom] / (sp["ms"][dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": CLASS_NAMES[dom], "achieved": achieved, "peak": peak,
                     "unit": "GB/s", "frac": achieved / peak,
+                    # same kernel class over the TIMED region itself (its launches are the whole step:
+                    # share_of_step): algorithmic bytes of those launches / CUDA-event time of the region
+                    "achieved_timed_region": timed_alg_gbs[dom],
                     "traffic": measured_traffic(CLASS_NAMES[dom], n - (world.bit_length() - 1)),
                     "traffic_source": "profiles/traffic.json (ncu --set full capture of this kernel, per amplitude)",
                     "peak_source": peak_src,

@@ -194,3 +194,26 @@ def test_global_gate_without_peers_is_refused():
     # diagonal gates and controls on global qubits need no peers
     passes = plan.describe(10, op.rz(0.3, 1 << 9) * op.x(1).c(1 << 9) * op.z(0x3FF), rank=1, world=2, peers=False)
     assert sum(len(p.all_ops()) for p in passes) == 2 + 10      # z(mask) is scheduled bit by bit
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_schedule_preserves_result(oracle, world):
+    """The order every RANK of a sharded register schedules (peer tile passes included) is a
+    reordering of commuting ops only: replayed through the oracle it gives the list-order state."""
+    n = 12
+    circ = workloads.mixed_all_kinds(n, 150, seed=9) * workloads.random_layered(n, 4)
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    v /= np.linalg.norm(v)
+    a = oracle.OracleReg.new(n)
+    a.write_amplitudes(v)
+    a.apply(circ)
+    want = a.amplitudes().copy()
+    for rank in range(world):
+        passes = plan.describe(n, circ, rank=rank, world=world, peers=True)
+        check_structure(passes, n, world, rank)
+        every_op_scheduled_once(passes, circ)
+        b = oracle.OracleReg.new(n)
+        b.write_amplitudes(v)
+        b.apply(planned_sequence(passes, circ))
+        assert np.abs(b.amplitudes() - want).max() <= 1e-12
