@@ -532,9 +532,15 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
         std::vector<StageSel> s2;
         while (!c2.empty()) {
             Slots sl;
-            const size_t room = ((size_t)TILE_MAX_OPS - (plan.mops.size() - cur.hdr.op_begin)) * 3 / 4;   // (+ run headers)
+            // Program size per pass, bounded by the CTA's shared memory next to the tile (tile.cu,
+            // tile_smem_bytes: 67 B per op, 48 B + 4 B x threads per stage): 2^12-amplitude tiles
+            // (64 KiB, 256 threads) leave room for half of what 2^11 tiles do.
+            const size_t max_ops = h.T >= 12 ? (size_t)TILE_MAX_OPS / 2 : (size_t)TILE_MAX_OPS;
+            const size_t max_stages = h.T >= 12 ? (size_t)TILE_MAX_STAGES / 2 : (size_t)TILE_MAX_STAGES;
+            const size_t used = plan.mops.size() - cur.hdr.op_begin;
+            const size_t room = used < max_ops ? (max_ops - used) * 3 / 4 : 0;      // (+ run headers)
             stage_select(pl, c2, set, room, s2, r2, sl, pass_fast && !getenv("QVNT_NO_LAZYX"));
-            if (s2.empty() || plan.stages.size() - cur.hdr.stage_begin >= (size_t)TILE_MAX_STAGES) {
+            if (s2.empty() || plan.stages.size() - cur.hdr.stage_begin >= max_stages) {
                 if (plan.mops.size() == cur.hdr.op_begin) {
                     set_error("internal: stage construction stalled");
                     return QVNT_ERR_UNSUPPORTED;

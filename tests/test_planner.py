@@ -217,3 +217,18 @@ def test_sharded_schedule_preserves_result(oracle, world):
         b.write_amplitudes(v)
         b.apply(planned_sequence(passes, circ))
         assert np.abs(b.amplitudes() - want).max() <= 1e-12
+
+
+@pytest.mark.parametrize("tile_bits,cap", [(12, 1024), (11, 2048)])
+def test_long_pass_programs_are_split(tile_bits, cap):
+    """A pass program must fit the CTA's shared memory next to the tile: very long runs of ops that
+    would all fit ONE pass (diagonal gates never constrain the tile) are cut into several passes."""
+    n = 16
+    circ = MultiOp()
+    for k in range(5000):
+        circ *= op.rz(0.001 * (k + 1), 1 << (k % n)).c(1 << ((k + 5) % n))
+    passes = plan.describe(n, circ, tile_bits=tile_bits)
+    assert sum(len(p.all_ops()) for p in passes) == 5000
+    assert len(passes) >= 3
+    for p in passes:
+        assert len(p.all_ops()) <= cap and len(p.stages) <= (32 if tile_bits >= 12 else 64)
