@@ -914,8 +914,8 @@ int describe_plan(uint32_t q_num, uint32_t rank, uint32_t world, int peers, int 
             continue;
         }
         const TPassHdr &h = pp.hdr;
-        snprintf(buf, sizeof(buf), "pass tile T=%u L=%u n_tiles=%llu base_or=%llu peer=%u fx_val=%llu gpos=", h.T, h.L,
-                 (unsigned long long)h.n_tiles, (unsigned long long)h.base_or, h.touches_peer,
+        snprintf(buf, sizeof(buf), "pass tile T=%u L=%u n_tiles=%llu base_or=%llu peer=%u full=%u fx_val=%llu gpos=",
+                 h.T, h.L, (unsigned long long)h.n_tiles, (unsigned long long)h.base_or, h.touches_peer, h.full,
                  (unsigned long long)h.fx.val);
         out += buf;
         for (uint32_t l = 0; l < h.T; ++l) out += std::to_string(h.gpos[l]) + (l + 1 < h.T ? "," : "");
@@ -928,9 +928,19 @@ int describe_plan(uint32_t q_num, uint32_t rank, uint32_t world, int peers, int 
             for (int j = 0; j < TILE_R; ++j) out += std::to_string(st.r_lpos[j]) + (j + 1 < TILE_R ? "," : "");
             out += " t=";
             for (uint32_t k = 0; k + TILE_R < h.T; ++k) out += std::to_string(st.t_lpos[k]) + (k + 1 + TILE_R < h.T ? "," : "");
-            out += "\n";
-            for (uint32_t o = st.op_begin; o < st.op_end; ++o)
+            out += " sync=" + std::to_string(st.sync_after_load) + "\n";
+            for (uint32_t o = st.op_begin; o < st.op_end; ++o) {
                 op_line(pl[plan.minfo[o].src], plan.minfo[o].form, plan.minfo[o].ra, plan.minfo[o].rb);
+                // the encoded micro-op exactly as the kernel reads it (tests/test_tile_emulator.py)
+                const MOp &m = plan.mops[o];
+                const MBase &b = plan.bases[o];
+                snprintf(buf, sizeof(buf),
+                         "mop code=%u flags=%u okmask=%u ctrl_thr=%u a_thr=%u a_reg=%u c0=%a c1=%a c2=%a c3=%a "
+                         "ctrl_base=%llu a_base=%llu\n",
+                         m.code, m.dagger, m.okmask, m.ctrl_thr, m.a_thr, m.a_reg, m.ph_re, m.ph_im, m.c2, m.c3,
+                         (unsigned long long)b.ctrl_base, (unsigned long long)b.a_base);
+                out += buf;
+            }
         }
     }
     return QVNT_OK;

@@ -25,10 +25,27 @@ class PlanOp:
 
 
 @dataclass
+class PlanMop:
+    """One encoded micro-op of a stage, as the kernel reads it (engine.h: MOp + MBase)."""
+    code: int
+    flags: int
+    okmask: int
+    ctrl_thr: int
+    a_thr: int
+    a_reg: int
+    c: List[float]
+    ctrl_base: int
+    a_base: int
+    src: int = -1
+
+
+@dataclass
 class PlanStage:
     r_lpos: List[int]
     t_lpos: List[int]
     ops: List[PlanOp] = field(default_factory=list)
+    mops: List[PlanMop] = field(default_factory=list)
+    sync: int = 0
 
 
 @dataclass
@@ -39,6 +56,7 @@ class PlanPass:
     n_tiles: int = 0
     base_or: int = 0
     peer: int = 0
+    full: int = 0
     fx_val: int = 0
     gpos: List[int] = field(default_factory=list)
     fx_pos: List[int] = field(default_factory=list)
@@ -65,6 +83,7 @@ def describe(q_num: int, circ, rank: int = 0, world: int = 1, peers: bool = Fals
     buf = ctypes.create_string_buffer(need.value)
     _ffi.check(lib.qvnt_plan_describe(*args, buf, need.value, byref(need)))
     passes: List[PlanPass] = []
+    last_src = -1
     for line in buf.value.decode().splitlines():
         tok = line.split()
         kv = dict(t.split("=", 1) for t in tok if "=" in t)
@@ -73,12 +92,21 @@ def describe(q_num: int, circ, rank: int = 0, world: int = 1, peers: bool = Fals
                 passes.append(PlanPass(direct=True))
             else:
                 passes.append(PlanPass(direct=False, T=int(kv["T"]), L=int(kv["L"]), n_tiles=int(kv["n_tiles"]),
-                                       base_or=int(kv["base_or"]), peer=int(kv["peer"]), fx_val=int(kv["fx_val"]),
+                                       base_or=int(kv["base_or"]), peer=int(kv["peer"]), full=int(kv.get("full", 0)),
+                                       fx_val=int(kv["fx_val"]),
                                        gpos=_ints(kv["gpos"]), fx_pos=_ints(kv["fx_pos"])))
         elif tok[0] == "stage":
-            passes[-1].stages.append(PlanStage(r_lpos=_ints(kv["r"]), t_lpos=_ints(kv["t"])))
+            passes[-1].stages.append(PlanStage(r_lpos=_ints(kv["r"]), t_lpos=_ints(kv["t"]),
+                                               sync=int(kv.get("sync", 0))))
+        elif tok[0] == "mop":
+            passes[-1].stages[-1].mops.append(PlanMop(
+                code=int(kv["code"]), flags=int(kv["flags"]), okmask=int(kv["okmask"]), ctrl_thr=int(kv["ctrl_thr"]),
+                a_thr=int(kv["a_thr"]), a_reg=int(kv["a_reg"]),
+                c=[float.fromhex(kv[k]) for k in ("c0", "c1", "c2", "c3")],
+                ctrl_base=int(kv["ctrl_base"]), a_base=int(kv["a_base"]), src=last_src))
         elif tok[0] == "op":
             o = PlanOp(**{k: int(v) for k, v in kv.items()})
+            last_src = o.src
             if o.form == 6:          # header of a merged diagonal run: not an op of its own
                 continue
             if passes[-1].direct:

@@ -1,0 +1,108 @@
+"""The planner's ENCODED micro-ops, executed by a numpy emulator of the kernel's fast stage
+interpreter (tests/tile_emulator.py), must reproduce the oracle's state: coefficient forms,
+slot / thread / tile splits of controls and diagonal masks, lazy x, merged diagonal runs, tile
+geometry -- and, for sharded registers, tile ownership and rank-dependent flags.  CPU only."""
+import numpy as np
+import pytest
+
+from qvnt_b200 import op, plan, workloads
+from qvnt_b200.op import MultiOp
+from tests import tile_emulator as emu
+from tests.test_planner import planned_sequence
+
+
+def _oracle_apply(oracle, n, psi, mop):
+    r = oracle.OracleReg.new(n)
+    r.write_amplitudes(psi)
+    r.apply(mop)
+    out = r.amplitudes().copy()
+    r.close()
+    return out
+
+
+def _emulate(oracle, n, circ, psi, world=1, **kw):
+    plans = [plan.describe(n, circ, rank=r, world=world, peers=world > 1, **kw) for r in range(world)]
+    n_fast = n_lazy = n_runs = 0
+    for k, p0 in enumerate(plans[0]):
+        if p0.direct or p0.full:
+            # direct sweeps and full-interpreter passes: their ops, in scheduled order, via the oracle
+            psi = _oracle_apply(oracle, n, psi, planned_sequence([p0], circ))
+            continue
+        n_fast += 1
+        for r in range(world):
+            p = plans[r][k]
+            assert not p.direct and not p.full and p.gpos == p0.gpos
+            emu.run_tile_pass(psi, p)
+        for st in p0.stages:
+            n_lazy += sum(1 for m in st.mops if m.code == emu.FC_LX)
+            n_runs += sum(1 for m in st.mops if m.code == emu.FC_DM)
+    return psi, n_fast, n_lazy, n_runs
+
+
+def _state(n, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+    return v / np.linalg.norm(v)
+
+
+def _fast_mix(n, layers, seed):
+    """Every kind the fast interpreter carries, with random controls (incl. multi-bit masks)."""
+    rng = workloads.SplitMix64(seed)
+    circ = MultiOp()
+    for _ in range(layers):
+        k = rng.next() % 11
+        b = 1 << (rng.next() % n)
+        m = (rng.next() & ((1 << n) - 1)) or 1
+        th = rng.angle()
+        g = [op.x(m), op.y(m), op.z(m), op.s(m), op.t(m), op.h(m), op.rx(th, b), op.ry(th, b), op.rz(th, b),
+             op.rzz(th, b | (1 << ((b.bit_length() + 2) % n)) if b != 1 << ((b.bit_length() + 2) % n) else b | (b << 1) % (1 << n) or 3),
+             op.t(m).dgr()][k]
+        if rng.next() % 3 == 0:
+            free = ((1 << n) - 1) & ~g.act_on()
+            for s_ in g:
+                free &= ~(s_.a_mask | s_.b_mask)
+            c = free & rng.next() & rng.next()
+            if c:
+                g = g.c(c)
+        circ *= g
+    return circ
+
+
+@pytest.mark.parametrize("n,circ_fn", [
+    (12, lambda n: workloads.random_layered(n, 8)),
+    (13, lambda n: op.qft((1 << n) - 1) * op.h((1 << n) - 1)),
+    (12, lambda n: _fast_mix(n, 250, seed=3)),
+    (14, lambda n: _fast_mix(n, 150, seed=4) * workloads.random_layered(n, 3)),
+])
+@pytest.mark.parametrize("tile_bits,chunk_bits", [(0, 0), (8, 3), (12, 7)])
+def test_encoded_plan_reproduces_oracle(oracle, n, circ_fn, tile_bits, chunk_bits):
+    circ = circ_fn(n)
+    v = _state(n, n)
+    want = _oracle_apply(oracle, n, v, circ)
+    got, n_fast, n_lazy, n_runs = _emulate(oracle, n, circ, v.copy(), tile_bits=tile_bits, chunk_bits=chunk_bits)
+    assert n_fast >= 1
+    assert np.abs(got - want).max() <= 1e-12
+
+
+def test_emulator_covers_lazy_x_and_merged_runs(oracle):
+    n = 13
+    circ = workloads.random_layered(n, 10) * op.qft((1 << n) - 1)
+    v = _state(n, 7)
+    got, n_fast, n_lazy, n_runs = _emulate(oracle, n, circ, v.copy())
+    assert n_lazy >= 5 and n_runs >= 3
+    assert np.abs(got - _oracle_apply(oracle, n, v, circ)).max() <= 1e-12
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_encoded_sharded_plan_reproduces_oracle(oracle, world):
+    """Every rank's tiles of every pass, emulated on the global state: ownership, peer chunks and
+    the flags derived from the rank bits."""
+    n = 13
+    top = n - 1
+    circ = workloads.random_layered(n, 6) * op.qft((1 << n) - 1) * _fast_mix(n, 80, seed=world)
+    circ *= op.x(1 << top).c(1 << 0) * op.rz(0.3, 1 << top).c(1 << (top - 1)) * op.h(1 << top) * op.x(1 << 2).c(1 << top)
+    v = _state(n, 11 + world)
+    want = _oracle_apply(oracle, n, v, circ)
+    got, n_fast, _, _ = _emulate(oracle, n, circ, v.copy(), world=world)
+    assert n_fast >= 2
+    assert np.abs(got - want).max() <= 1e-12
