@@ -1,0 +1,64 @@
+#!/usr/bin/env python
+"""Micro-op composition of a workload's schedule (host only, no GPU): passes, stages, and how many
+ops run as which arm of the fast stage interpreter -- the instruction-cost model behind
+DESIGN.md section 9 (pair / diagonal arms: 64 FP64 instr per thread; register-swap x: 96 moves;
+lazy x: 3 instr; merged diagonal run members: ~20 instr)."""
+import argparse
+import collections
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from qvnt_b200 import plan, workloads  # noqa: E402
+
+NAMES = {0: "pair_real", 4: "pair_cross", 8: "swap_x", 12: "diag_thread", 13: "diag_slot", 17: "diag_generic",
+         18: "pair_addsub(h)", 22: "lazy_x", 23: "diag_run_header"}
+COST = {"pair_real": 110, "pair_cross": 112, "pair_addsub(h)": 110, "diag_thread": 110, "diag_slot": 110,
+        "diag_generic": 150, "swap_x": 80,      # (96 moves + 46 where the control holds, ~20 elsewhere)
+        "lazy_x": 25, "diag_run_header": 110, "diag_run_member": 20}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="random28", choices=["random28", "qft", "qft_h"])
+    ap.add_argument("--qubits", type=int, default=28)
+    ap.add_argument("--depth", type=int, default=100)
+    ap.add_argument("--world", type=int, default=1)
+    ap.add_argument("--tile-bits", type=int, default=0)
+    ap.add_argument("--chunk-bits", type=int, default=0)
+    a = ap.parse_args()
+    n = a.qubits
+    circ = (workloads.random_layered(n, a.depth) if a.workload == "random28"
+            else workloads.qft_full(n) if a.workload == "qft" else workloads.qft_plus_h(n))
+    ps = plan.describe(n, circ, world=a.world, peers=a.world > 1, tile_bits=a.tile_bits, chunk_bits=a.chunk_bits)
+    cnt = collections.Counter()
+    full = direct = 0
+    for p in ps:
+        if p.direct:
+            direct += 1
+            continue
+        if p.full:
+            full += 1
+        for st in p.stages:
+            skip = 0
+            for m in st.mops:
+                if skip:
+                    cnt["diag_run_member"] += 1
+                    skip -= 1
+                    continue
+                c = m.code - 24 if m.code >= 24 else m.code
+                base = max(k for k in NAMES if k <= c)
+                cnt[NAMES[base]] += 1
+                if base == 23:
+                    skip = m.a_reg
+    s = plan.summary(ps)
+    print(f"{len(circ)} SingleOps -> {s['passes']} passes ({direct} direct, {full} full-interpreter, "
+          f"{s['peer_passes']} peer), {s['stages']} stages, {s['ops_per_pass']:.1f} ops/pass")
+    tot = sum(COST.get(k, 110) * v for k, v in cnt.items())
+    for k, v in cnt.most_common():
+        print(f"  {k:18s} {v:6d}   ~{COST.get(k, 110) * v / max(tot, 1) * 100:4.1f} % of the per-thread instruction work")
+
+
+if __name__ == "__main__":
+    main()
