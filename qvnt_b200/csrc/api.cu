@@ -143,6 +143,7 @@ static int create_common(uint32_t q_num, uint64_t state, uint32_t rank, uint32_t
         return QVNT_ERR_INVALID;
     }
     QV_CUDA(cudaSetDevice(device));
+    if (tile_kernel_setup() != 0) return cuda_fail(cudaGetLastError(), "tile kernel attributes");
     qvnt_reg *r = new (std::nothrow) qvnt_reg();
     if (!r) return QVNT_ERR_OOM;
     r->device = device;
@@ -344,7 +345,8 @@ int qvnt_reg_clone(qvnt_reg_t *r, qvnt_reg_t **out) {
     c->opt_fuse = r->opt_fuse;
     c->opt_tile_bits = r->opt_tile_bits;
     c->opt_chunk_bits = r->opt_chunk_bits;
-    c->opt_tma = r->opt_tma;
+    c->knobs = r->knobs;
+    c->rng_state = r->rng_state;
     return QVNT_OK;
 }
 
@@ -604,8 +606,8 @@ int qvnt_reg_set_option(qvnt_reg_t *r, const char *key, int64_t value) {
     if (!r || !key) return QVNT_ERR_INVALID;
     if (!strcmp(key, "fuse")) r->opt_fuse = value != 0;
     else if (!strcmp(key, "tile_bits")) {
-        if (value != 0 && (value < 8 || value > TILE_MAX_BITS)) {
-            set_error("tile_bits must be 0 (auto) or 8..%d", TILE_MAX_BITS);
+        if (value != 0 && (value < 6 || value > TILE_MAX_BITS)) {
+            set_error("tile_bits must be 0 (auto) or 6..%d", TILE_MAX_BITS);
             return QVNT_ERR_INVALID;
         }
         r->opt_tile_bits = (int)value;
@@ -615,11 +617,15 @@ int qvnt_reg_set_option(qvnt_reg_t *r, const char *key, int64_t value) {
             return QVNT_ERR_INVALID;
         }
         r->opt_chunk_bits = (int)value;
-    } else if (!strcmp(key, "tma")) r->opt_tma = value != 0;
-    else if (!strcmp(key, "tile_nbuf")) g_tile_nbuf = (int)value;
-    else if (!strcmp(key, "tile_stagger")) g_tile_stagger = (int)value;
-    else if (!strcmp(key, "tile_sysload")) g_tile_sysload = (int)value;
-    else if (!strcmp(key, "profile")) {
+    } else if (!strcmp(key, "tma")) r->knobs.bulk = value != 0;
+    else if (!strcmp(key, "prefetch")) r->knobs.prefetch = value != 0;
+    else if (!strcmp(key, "tile_ctas")) {
+        if (value != 0 && (value < 3 || value > 5)) {
+            set_error("tile_ctas must be 0 (auto) or 3..5");
+            return QVNT_ERR_INVALID;
+        }
+        r->knobs.ctas_per_sm = (int)value;
+    } else if (!strcmp(key, "profile")) {
         int rc = use(r);
         if (rc) return rc;
         if (!value) fold_timed(r);

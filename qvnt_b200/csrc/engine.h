@@ -62,6 +62,7 @@ enum TForm : uint32_t {
     TF_ODD2 = 3,    // swap family: odd-parity pair {slot ra set, slot rb set}
     TF_QUAD = 4,    // h2/u2: a = slot ra, b = slot rb
     TF_LAZYX = 5,   // x between threads: no register slot
+    TF_LAZYI = 7,   // x on a register slot, no control in a slot: the slot is marked inverted
     TF_GROUP = 6    // header of a merged diagonal run (not an op of its own)
 };
 
@@ -79,45 +80,62 @@ enum MCode : uint8_t {
 };
 
 // Dispatch codes of the FAST stage interpreter (tile.cu): passes made only of the common kinds
-// (x, y, rx, ry, h1 on one bit; z/s/t on one bit; rz; rzz) are lowered by the planner to five
+// (x, y, rx, ry, h1 on one bit; z/s/t on one bit; rz; rzz) are lowered by the planner to a few
 // coefficient-driven forms, so one arm serves several kinds:
-//   FC_PR  real pair      new0 = c0*p0 + c1*p1 ; new1 = c2*p0 + c3*p1            (ry)
+//   FC_PR  real pair      new0 = c0*p0 + c1*p1 ; new1 = c2*p0 + c3*p1            (ry, h1)
 //   FC_PX  crossed pair   new0 = c0*p0 - i*c1*p1 ; new1 = -i*c2*p0 + c3*p1        (rx, y)
-//   FC_SW  swap           new0 = p1 ; new1 = p0                                   (x)
 //   FC_DU / FC_DS / FC_DG diagonal: p *= (parity of i & target ? f1 : f0), f0 = (c0,c1), f1 = (c2,c3);
 //          DU: no target bit in a register slot; DS: exactly one (slot j); DG: any a_reg
+//   FC_SW  x whose target AND a control sit in register slots: the selected pairs trade places
+//   FC_LX / FC_LI  "lazy" x: a permutation that costs no data movement, see below
+// The codes are DENSE (0 .. FC_COUNT-1, + FC_MASKED variants) so the interpreter's switch is one
+// jump table.
 enum FCode : uint8_t {
     FC_PR = 0,    // + slot
     FC_PX = 4,    // + slot
-    FC_SW = 8,    // + slot
+    FC_DS = 8,    // + slot
     FC_DU = 12,
-    FC_DS = 13,   // + slot
-    FC_DG = 17,
-    FC_PA = 18,   // + slot: add/sub pair  new0 = (p0 + p1) * c0 ; new1 = (p0 - p1) * c0   (h1: the
-                  //         reference's own operation order, h1.rs:16-22; h2 halves use c0 = 1 and 0.5)
-    FC_LX = 22,   // lazy x: target and controls on thread / outer bits (a_thr = target's thread bit,
-                  //         a_reg = its tile-local position); no register slot involved
-    FC_DM = 23,   // header of a run of a_reg (in MOp::a_reg) diagonal ops that share their controls and
-                  //         have no target bit in a register slot: their factors are multiplied into ONE
-                  //         complex number per thread, applied to the 16 amplitudes once
-    FC_COUNT = 24,
-    FC_ALL = 24   // added to the code when no control sits in a register slot (okmask == 0xFFFF)
+    FC_DG = 13,
+    FC_LX = 14,   // lazy x, target on a thread bit: target and controls on thread / outer bits (a_thr =
+                  //         target's thread bit, a_reg = its tile-local position | position in the shard << 8);
+                  //         the thread flips the bit in the index it will STORE its amplitudes to
+    FC_LI = 15,   // lazy x, target in register slot j (a_reg = j), controls on thread /
+                  //         outer bits: the thread marks slot j as inverted -- its register K now holds the
+                  //         amplitude of slot pattern K ^ (1 << j).  Later ops on that slot read their
+                  //         coefficients from the descriptor's `alt` block (roles of the pair exchanged),
+                  //         and the stage's stores go to the exchanged addresses.  3 instructions.
+    FC_DM = 16,   // header of a run of a_reg diagonal ops that share their controls and have no target
+                  //         bit in a register slot: their factors are multiplied into ONE complex number
+                  //         per thread, applied to the 16 amplitudes once
+    FC_COUNT = 17,
+    FC_MASKED = 17, // added to FC_PR / FC_PX / FC_DS / FC_DU / FC_DG / FC_DM codes when a control sits in a
+                    // register slot (okmask != 0xFFFF): per-slot-pattern predicates
+    FC_SW = 34,   // + slot (always masked)
+    FC_TOTAL = 38
 };
-constexpr uint8_t MOP_SKIP0 = 0x02;   // MOp::dagger bit 1 (fast diagonal forms): f0 == 1, even parity untouched
+constexpr uint8_t MOP_SKIP0 = 0x02;   // flags bit 1 (diagonal forms): f0 == 1, even parity untouched
+constexpr uint8_t MOP_COND = 0x04;    // flags bit 2: the op has controls on thread bits or outside the tile
+                                      //   (ctrl_thr != 0 or ctrl_base != 0): test before dispatch
+constexpr uint8_t MOP_PARB = 0x08;    // flags bit 3 (diagonal forms): target bits outside the tile (a_base != 0):
+                                      //   the per-tile flag byte carries their parity
+constexpr uint8_t MOP_CONDB = 0x10;   // flags bit 4: ... and some of them outside the tile (ctrl_base != 0): read the flag byte
+constexpr uint32_t MOP_ALT_BYTES = 32; // byte distance from the coefficient block to the `alt` block
 
-struct __align__(16) MOp {   // 48 bytes, staged in shared memory
+struct __align__(16) MOp {   // 80 bytes, staged in shared memory
     uint8_t code;        // MCode (full interpreter) or FCode (fast interpreter)
-    uint8_t dagger;      // bit 0: dagger; bit 1: MOP_SKIP0
+    uint8_t dagger;      // bit 0: dagger (full); fast: MOP_* flags
     uint16_t okmask;     // bit K: register slot pattern K satisfies the controls held in register slots
     uint32_t ctrl_thr;   // controls on thread bits (bit k = thread bit k of the stage)
     uint32_t a_thr;      // diagonal class: target-mask bits on thread bits; u1/u2: matrix table index
-    uint16_t a_reg;      // diagonal class: target-mask bits on register slots
-    uint16_t _pad;
+    uint16_t a_reg;      // diagonal class: target-mask bits on register slots (LX / LI / DM: see FCode)
+    uint16_t idx;        // the op's index inside its pass (per-tile flag byte)
     double ph_re, ph_im; // full: (cos t/2, sin t/2); fast: c0, c1
     double c2, c3;       // fast only
+    double alt[4];       // fast only: the coefficients to use while the op's register slot is inverted
+                         // (FC_LI): pair forms (c3, c2, c1, c0); FC_DS (c2, c3, c0, c1)
 };
-static_assert(sizeof(MOp) == 48, "MOp layout");
-constexpr uint32_t MOP_BYTES = 48;
+static_assert(sizeof(MOp) == 80, "MOp layout");
+constexpr uint32_t MOP_BYTES = 80;
 
 struct MBase {           // per-op masks over the index bits that are NOT tile bits (global numbering)
     uint64_t ctrl_base;
@@ -148,18 +166,23 @@ struct TPassHdr {
     uint64_t base_or;            // this rank's bits for the global qubits that are NOT tile bits
     uint32_t touches_peer;       // some tile bit is a rank bit
     uint32_t full;               // some op needs the full interpreter (u1/u2, two-bit pair ops, multi-bit masks)
-    uint32_t waves, stagger_cycles;   // filled by launch_tile_pass: CTAs per SM, start offset between them
-    uint32_t sysload, _pad2;
+    uint32_t need_flags;         // some op of the pass depends on index bits outside the tile (per-tile flag bytes)
+    uint32_t prefetch;           // filled by launch_tile_pass (TileKnobs): L2 prefetch of the next tile's chunks
+    uint64_t fixed_mask;         // local index bits the tile counter does NOT enumerate (tile bits + ownership bits)
     uint16_t stage_end[TILE_MAX_STAGES];   // ops of stage s: [stage_end[s-1], stage_end[s]) relative to op_begin
     Fixed fx;                    // the same enumeration bit by bit (host side: describe / tests)
 };
 
+// Per-handle tuning knobs of the tile pass (qvnt_reg_set_option): no process-global state.
+struct TileKnobs {
+    int ctas_per_sm = 0;   // 0 = auto (4 for 2^11 tiles, 2 for 2^12); 3 / 5: forced
+    int bulk = 1;          // 1: tile loads by cp.async.bulk (TMA) + mbarrier; 0: 16-byte cp.async
+    int prefetch = 1;      // 1: cp.async.bulk.prefetch.L2 of tile i+1 while tile i computes
+};
 int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, const TStage *d_stages,
-                     const MOp *d_ops, const MBase *d_bases, const amp *mat_table, int sm_count);
-int tile_kernel_setup();
-extern int g_tile_nbuf;
-extern int g_tile_stagger;
-extern int g_tile_sysload;
+                     const MOp *d_ops, const MBase *d_bases, const amp *mat_table, int sm_count,
+                     const TileKnobs &knobs);
+int tile_kernel_setup();   // once per process and device (qvnt_reg_create)
 
 // ---- measurement / utility kernels (measure.cu) -----------------------------
 constexpr int REDUCE_BLOCKS_MAX = 4096;

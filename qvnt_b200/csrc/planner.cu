@@ -145,7 +145,8 @@ static int lower_ops(const PlanCfg &r, const qvnt_op_t *ops, size_t n_ops, std::
                 q.cls = CLS_PAIR;
                 q.d.a = half ? o.b_mask : o.a_mask;
                 q.d.b = 0;
-                q.d.ph_re = half ? 0.5 : 1.0;      // h2.rs:37 scales the sum of four once, by 0.5
+                q.d.ph_re = half ? 0.5 : 1.0;      // h2.rs:37 scales the sum of four once, by 0.5 (exact powers of
+                                                   // two: the golden vectors of quant.rs:653-673 stay bit-exact)
                 q.d.ph_im = 0.0;
                 q.mix = q.d.a;
                 q.dg = q.d.ctrl;
@@ -332,10 +333,6 @@ static void stage_select(const std::vector<POp> &pl, const std::vector<int> &can
     uint64_t bw = 0, br = 0;
     sel.clear();
     rest.clear();
-    // later_work[i]: some op after cand[i] is not an x (so a later stage will exist anyway)
-    std::vector<char> later_work(cand.size() + 1, 0);
-    for (size_t k = cand.size(); k-- > 0;)
-        later_work[k] = later_work[k + 1] || pl[cand[k]].d.kind != QVNT_X;
     size_t i = 0;
     for (; i < cand.size(); ++i) {
         const POp &p = pl[cand[i]];
@@ -352,8 +349,6 @@ static void stage_select(const std::vector<POp> &pl, const std::vector<int> &can
                 sel.push_back({cand[i], -1, -1});
                 continue;
             }
-            if (getenv("QVNT_LAZYX_DEFER") && (bits & slot_bits) && room && (later_work[i + 1] || !rest.empty()))
-                conflict = true;                                          // wait for a stage where it is lazy
         }
         if (!conflict) {
             Slots trial = sl;
@@ -392,6 +387,7 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
     if (L > n_local) L = n_local;
     if (L > T) L = T;
     if (T - L > (uint32_t)TILE_MAX_HIGH) L = T - TILE_MAX_HIGH;
+    if (L + 2 > T) L = T >= 2 ? T - 2 : 0;      // keep room for the two gathered bits a two-qubit op may need
     const bool tile_ok = T >= (uint32_t)TILE_MIN_BITS && n_local >= (uint32_t)TILE_MIN_BITS;
     const uint64_t low = (1ull << L) - 1ull;
     const uint64_t rank_bits = (uint64_t)c.rank << n_local;
@@ -427,6 +423,14 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
             set = low | first.mix;
         } else {
             greedy_select(pl, cand, low, allowed, (int)(T - L), qmask, 1u << 16, sel, rest, set);
+        }
+        if (sel.empty() && !first_global) {
+            // no tile geometry holds the op's mix bits (tiny shards): one direct sweep
+            pp.direct = true;
+            pp.ops.push_back(cand[0]);
+            cand.erase(cand.begin());
+            passes.push_back(pp);
+            continue;
         }
         if (sel.empty()) {
             set_error("internal: planner could not place op kind %u (mix 0x%llx) in a tile", first.d.kind,
@@ -510,6 +514,8 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
             k = e;
         }
         h.fx_val = h.fx.val;
+        h.fixed_mask = 0;
+        for (uint32_t k = 0; k < h.fx.n; ++k) h.fixed_mask |= 1ull << h.fx.pos[k];
 
         bool pass_fast = true;
         for (int idx : pp.ops) pass_fast = pass_fast && fast_kind(pl[idx]);
@@ -523,6 +529,12 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
             cur.hdr.n_ops = (uint32_t)plan.mops.size() - cur.hdr.op_begin;
             for (uint32_t k = 0; k < cur.hdr.n_stages; ++k)
                 cur.hdr.stage_end[k] = (uint16_t)(plan.stages[cur.hdr.stage_begin + k].op_end - cur.hdr.op_begin);
+            cur.hdr.need_flags = 0;
+            for (uint32_t k = 0; k < cur.hdr.n_ops; ++k) {
+                plan.mops[cur.hdr.op_begin + k].idx = (uint16_t)k;
+                const MBase &mb = plan.bases[cur.hdr.op_begin + k];
+                if (mb.ctrl_base | mb.a_base) cur.hdr.need_flags = 1;
+            }
             if (cur.hdr.n_ops) out_passes.push_back(cur);
             cur.ops.clear();
             cur.hdr.stage_begin = (uint32_t)plan.stages.size();
@@ -539,7 +551,7 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
             const size_t max_stages = h.T >= 12 ? (size_t)TILE_MAX_STAGES / 2 : (size_t)TILE_MAX_STAGES;
             const size_t used = plan.mops.size() - cur.hdr.op_begin;
             const size_t room = used < max_ops ? (max_ops - used) * 3 / 4 : 0;      // (+ run headers)
-            stage_select(pl, c2, set, room, s2, r2, sl, pass_fast && !getenv("QVNT_NO_LAZYX"));
+            stage_select(pl, c2, set, room, s2, r2, sl, pass_fast);
             if (s2.empty() || plan.stages.size() - cur.hdr.stage_begin >= max_stages) {
                 if (plan.mops.size() == cur.hdr.op_begin) {
                     set_error("internal: stage construction stalled");
@@ -564,21 +576,28 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
             TStage st;
             memset(&st, 0, sizeof(st));
             for (int j = 0; j < TILE_R; ++j) st.r_lpos[j] = (uint8_t)lpos_of[sl.bit[j]];
-            // thread bits: lane bits 0..2 take tile-local bits congruent to 0,1,2 mod 3 so the
-            // swizzled quarter-warp access is bank-conflict free; the rest ascend
+            // thread bits: lane bit j (j = 0..2) takes tile-local bit j or L + j -- in the padded-linear
+            // tile buffer (tile.cu) those move an address by 2^j bank groups, so a quarter-warp's eight
+            // 16-byte accesses fall into eight different groups; the rest ascend
             std::vector<int> order;
             {
                 std::vector<int> nr;
                 for (uint32_t l = 0; l < h.T; ++l)
                     if (!((rset >> h.gpos[l]) & 1)) nr.push_back((int)l);
                 std::vector<char> used(nr.size(), 0);
-                for (int j = 0; j < 3; ++j)
-                    for (size_t i = 0; i < nr.size(); ++i)
-                        if (!used[i] && nr[i] % 3 == j) {
-                            used[i] = 1;
-                            order.push_back(nr[i]);
-                            break;
-                        }
+                for (int j = 0; j < 3; ++j) {
+                    int pick = -1;
+                    for (size_t i = 0; i < nr.size() && pick < 0; ++i)
+                        if (!used[i] && nr[i] == j) pick = (int)i;
+                    for (size_t i = 0; i < nr.size() && pick < 0; ++i)
+                        if (!used[i] && nr[i] == (int)h.L + j) pick = (int)i;
+                    for (size_t i = 0; i < nr.size() && pick < 0; ++i)
+                        if (!used[i]) pick = (int)i;
+                    if (pick >= 0) {
+                        used[pick] = 1;
+                        order.push_back(nr[pick]);
+                    }
+                }
                 for (size_t i = 0; i < nr.size(); ++i)
                     if (!used[i]) order.push_back(nr[i]);
                 for (size_t i = 0; i < order.size(); ++i) st.t_lpos[i] = (uint8_t)order[i];
@@ -619,11 +638,19 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                     const bool dg = p.d.dagger != 0;
                     double f0r = 1.0, f0i = 0.0, f1r = 1.0, f1i = 0.0;
                     mi.form = p.cls == CLS_DIAG ? TF_DIAG : TF_PAIR1;
+                    m.dagger = 0;       // fast forms: MOP_* flags only
+                    auto pair4 = [&](uint8_t code, double c0, double c1, double c2, double c3) {
+                        m.code = (uint8_t)(code + ss.ra);
+                        m.ph_re = c0; m.ph_im = c1; m.c2 = c2; m.c3 = c3;
+                        // the same 2x2 with the roles of the pair's members exchanged (slot inverted, FC_LI)
+                        m.alt[0] = c3; m.alt[1] = c2; m.alt[2] = c1; m.alt[3] = c0;
+                    };
                     switch (p.d.kind) {
-                    case QVNT_H1: m.code = (uint8_t)(FC_PA + ss.ra); m.ph_re = c; break;
-                    case QVNT_RY: m.code = (uint8_t)(FC_PR + ss.ra); m.ph_re = c; m.ph_im = -sn; m.c2 = sn; m.c3 = c; break;
-                    case QVNT_RX: m.code = (uint8_t)(FC_PX + ss.ra); m.ph_re = c; m.ph_im = sn; m.c2 = sn; m.c3 = c; break;
-                    case QVNT_Y: m.code = (uint8_t)(FC_PX + ss.ra); m.ph_re = 0.0; m.ph_im = 1.0; m.c2 = -1.0; m.c3 = 0.0; break;
+                    // h1.rs:16-22: (p0 + p1) * s, (p0 - p1) * s
+                    case QVNT_H1: pair4(FC_PR, c, c, c, -c); break;
+                    case QVNT_RY: pair4(FC_PR, c, -sn, sn, c); break;
+                    case QVNT_RX: pair4(FC_PX, c, sn, sn, c); break;
+                    case QVNT_Y: pair4(FC_PX, 0.0, 1.0, -1.0, 0.0); break;
                     case QVNT_X:
                         if (ss.ra < 0) {
                             uint32_t treg, tthr;
@@ -635,6 +662,11 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                             m.a_reg = (uint16_t)(lpos_of[ctz64(p.d.a)] | (ctz64(p.d.a) << 8));
                             mi.form = TF_LAZYX;
                             mi.ra = mi.rb = 0;
+                        } else if (creg == 0) {
+                            // no control in a register slot: the thread marks the slot as inverted
+                            m.code = (uint8_t)FC_LI;
+                            m.a_reg = (uint16_t)ss.ra;
+                            mi.form = TF_LAZYI;
                         } else {
                             m.code = (uint8_t)(FC_SW + ss.ra);
                         }
@@ -652,10 +684,14 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                         m.code = areg == 0 ? (uint8_t)FC_DU
                                  : pc64(areg) == 1 ? (uint8_t)(FC_DS + ctz64(areg)) : (uint8_t)FC_DG;
                         m.ph_re = f0r; m.ph_im = f0i; m.c2 = f1r; m.c3 = f1i;
+                        m.alt[0] = f1r; m.alt[1] = f1i; m.alt[2] = f0r; m.alt[3] = f0i;
                         if (f0r == 1.0 && f0i == 0.0) m.dagger |= MOP_SKIP0;
+                        if (b.a_base) m.dagger |= MOP_PARB;
                         mi.ra = mi.rb = 0;
                     }
-                    if (m.okmask == 0xFFFFu && m.code != (uint8_t)FC_LX) m.code = (uint8_t)(m.code + FC_ALL);
+                    if (cthr || b.ctrl_base) m.dagger |= MOP_COND;
+                    if (b.ctrl_base) m.dagger |= MOP_CONDB;
+                    if (m.okmask != 0xFFFFu && m.code < (uint8_t)FC_SW) m.code = (uint8_t)(m.code + FC_MASKED);
                 } else if (p.cls == CLS_DIAG) {
                     uint32_t areg, athr;
                     split(p.d.a, areg, athr, b.a_base);
@@ -725,7 +761,7 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                 plan.bases.resize(b0);
                 plan.minfo.resize(b0);
                 auto is_du = [&](size_t k) {
-                    return mo[k].code == (uint8_t)FC_DU || mo[k].code == (uint8_t)(FC_ALL + FC_DU);
+                    return mo[k].code == (uint8_t)FC_DU || mo[k].code == (uint8_t)(FC_MASKED + FC_DU);
                 };
                 for (size_t k = 0; k < mo.size();) {
                     size_t e = k;
@@ -740,7 +776,8 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                         MBase hb;
                         memset(&hd, 0, sizeof(hd));
                         memset(&hb, 0, sizeof(hb));
-                        hd.code = (uint8_t)FC_DM;
+                        hd.code = (uint8_t)(mo[k].okmask == 0xFFFFu ? FC_DM : FC_DM + FC_MASKED);
+                        hd.dagger = (uint8_t)(mo[k].dagger & (MOP_COND | MOP_CONDB));
                         hd.okmask = mo[k].okmask;
                         hd.ctrl_thr = mo[k].ctrl_thr;
                         hd.a_reg = (uint16_t)(e - k);
@@ -793,7 +830,6 @@ static int run_plan(qvnt_reg *r, const std::vector<POp> &pl, Plan &plan) {
         d_stages = (TStage *)r->d_ops;
         d_mops = (MOp *)((char *)r->d_ops + sb_al);
         d_bases = (MBase *)((char *)r->d_ops + sb_al + ob_al);
-        if (tile_kernel_setup() != 0) return cuda_fail(cudaGetLastError(), "tile kernel attribute");
     }
 
     // ---- enqueue ----
@@ -816,7 +852,7 @@ static int run_plan(qvnt_reg *r, const std::vector<POp> &pl, Plan &plan) {
         }
         need_barrier = h.touches_peer != 0;
         LaunchScope ls(r, 1);
-        int n = launch_tile_pass(r->stream, r->segs, h, d_stages, d_mops, d_bases, r->d_mat, r->sm_count);
+        int n = launch_tile_pass(r->stream, r->segs, h, d_stages, d_mops, d_bases, r->d_mat, r->sm_count, r->knobs);
         ls.done(n);
         if (n < 0) {
             cudaError_t e = cudaGetLastError();
@@ -900,11 +936,12 @@ int describe_plan(uint32_t q_num, uint32_t rank, uint32_t world, int peers, int 
     if (rc) return rc;
     Plan plan;
     if ((rc = build_plan(c, pl, plan))) return rc;
-    char buf[512];
+    char buf[1024];
     auto op_line = [&](const POp &p, int form, int ra, int rb) {
-        snprintf(buf, sizeof(buf), "op src=%u kind=%u dagger=%u a=%llu b=%llu ctrl=%llu form=%d ra=%d rb=%d\n", p.src,
-                 p.d.kind, p.d.dagger, (unsigned long long)p.d.a, (unsigned long long)p.d.b,
-                 (unsigned long long)p.d.ctrl, form, ra, rb);
+        // scale: the butterfly factor of an h1 (1/sqrt2; the halves of a split h2 carry 1 and 0.5)
+        snprintf(buf, sizeof(buf), "op src=%u kind=%u dagger=%u a=%llu b=%llu ctrl=%llu form=%d ra=%d rb=%d scale=%a\n",
+                 p.src, p.d.kind, p.d.dagger, (unsigned long long)p.d.a, (unsigned long long)p.d.b,
+                 (unsigned long long)p.d.ctrl, form, ra, rb, p.d.kind == QVNT_H1 ? p.d.ph_re : 0.0);
         out += buf;
     };
     for (const PassPlan &pp : plan.passes) {
@@ -935,10 +972,11 @@ int describe_plan(uint32_t q_num, uint32_t rank, uint32_t world, int peers, int 
                 const MOp &m = plan.mops[o];
                 const MBase &b = plan.bases[o];
                 snprintf(buf, sizeof(buf),
-                         "mop code=%u flags=%u okmask=%u ctrl_thr=%u a_thr=%u a_reg=%u c0=%a c1=%a c2=%a c3=%a "
-                         "ctrl_base=%llu a_base=%llu\n",
-                         m.code, m.dagger, m.okmask, m.ctrl_thr, m.a_thr, m.a_reg, m.ph_re, m.ph_im, m.c2, m.c3,
-                         (unsigned long long)b.ctrl_base, (unsigned long long)b.a_base);
+                         "mop code=%u flags=%u okmask=%u ctrl_thr=%u a_thr=%u a_reg=%u idx=%u c0=%a c1=%a c2=%a c3=%a "
+                         "a0=%a a1=%a a2=%a a3=%a ctrl_base=%llu a_base=%llu\n",
+                         m.code, m.dagger, m.okmask, m.ctrl_thr, m.a_thr, m.a_reg, m.idx, m.ph_re, m.ph_im, m.c2, m.c3,
+                         m.alt[0], m.alt[1], m.alt[2], m.alt[3], (unsigned long long)b.ctrl_base,
+                         (unsigned long long)b.a_base);
                 out += buf;
             }
         }

@@ -49,7 +49,7 @@ struct qvnt_reg {
     int opt_fuse = 1;
     int opt_tile_bits = 0;          // 0 = auto
     int opt_chunk_bits = 0;         // 0 = auto
-    int opt_tma = 1;
+    qv::TileKnobs knobs;            // "tma" / "tile_ctas"
     int opt_profile = 0;
     uint64_t rng_state = 0x51564E54ull;
 

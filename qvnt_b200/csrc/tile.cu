@@ -8,28 +8,35 @@
 // pass the HBM traffic is 16 B read + 16 B written per amplitude, whatever the number
 // of gates carried.
 //
-// Layout of a tile: T tile bits = low L bits (contiguous 16*2^L-byte chunks, loaded with
-// coalesced 16-byte cp.async) + T-L gathered high bits.  A gathered bit may be a rank bit
-// of a sharded register: that chunk is then read from / written to the peer GPU's HBM
-// through its NVLink-mapped pointer (Segs), so a global-qubit gate needs no separate
-// exchange step -- the "swap" is the tile's own load and store.
+// Layout of a tile: T tile bits = low L bits (contiguous 16*2^L-byte chunks) + T-L gathered high
+// bits.  A gathered bit may be a rank bit of a sharded register: that chunk is then read from /
+// written to the peer GPU's HBM through its NVLink-mapped pointer (Segs), so a global-qubit gate
+// needs no separate exchange step -- the "swap" is the tile's own load and store.
 //
-// Shared memory is XOR-swizzled at 16-byte granularity (slot ^= fold of the upper index
-// bits into the low 3) so that, whichever bits a stage keeps in registers, the 8 lanes
-// of a quarter-warp hit 8 different 16-byte bank groups (the planner picks the lane bits).
-// The swizzle is GF(2)-linear, so a thread's 16 slot addresses are one base XOR 16
-// stage-uniform constants.
+// Tile loads are TMA bulk copies: one `cp.async.bulk.shared.global` per chunk, issued by the lanes
+// of warp 0, completing on an mbarrier every thread of the CTA waits on (SASS: UBLKCP + SYNCS).
+// No thread spends instructions or registers on the load, and the data lands while the CTA runs
+// the last stage of the previous tile.  (Option "bulk" = 0 keeps a 16-byte cp.async path for A/B
+// measurements.)
+//
+// Shared-memory layout: chunk c lives at byte offset c * (16 * 2^L + 16) -- chunks stay linear (a
+// bulk copy needs that) and ONE 16-byte pad per chunk rotates the bank group of consecutive
+// chunks.  The address of tile-local index j is 16 * (j + (j >> L)): additive in the index bits,
+// so the 16 addresses of a thread are one base plus stage-uniform constants.  A quarter-warp
+// (8 lanes, 128 bytes) is conflict free when the three low lane bits are tile-local bits of the
+// classes {0, L}, {1, L+1}, {2, L+2}; the planner assigns them that way whenever the stage's
+// register slots leave one bit of each class free.
 //
 // Stages.  A stage keeps TILE_R = 4 tile bits in "register slots": every thread holds the 16
 // amplitudes that differ in those bits, runs all of the stage's ops on them and only then touches
 // shared memory again.  The last stage of a pass stores its registers straight to HBM, so the tile
-// buffer is free as soon as that stage has read it and the next tile's cp.async loads are issued
-// there.  An op is a 48-byte MOp in shared memory whose `code` selects a fully unrolled arm;
-// everything that depends on the amplitude index was split by the planner into
+// buffer is free as soon as that stage has read it and the next tile's load is issued there.
+// An op is an 80-byte MOp in shared memory whose `code` selects a fully unrolled arm through ONE
+// jump table; everything that depends on the amplitude index was split by the planner into
 //   - register-slot part: compile-time per arm, or a 16-bit `okmask` (controls in register slots),
-//   - thread part: one AND/compare on the thread's group number per op,
+//   - thread part: one AND/compare on the thread's group number, only for ops flagged MOP_COND,
 //   - tile part: one flag byte per op per tile (controls / diagonal-mask bits outside the
-//     tile), computed once per tile.
+//     tile), computed once per tile and only for passes that have such ops (hdr.need_flags).
 // Tiles none of whose ops is active (multi-controlled gates) are skipped without being read.
 //
 // Two interpreters share the plumbing: the FULL one carries every kind with the reference's
@@ -41,10 +48,13 @@
 // sweeps (direct.cu, -fmad=false) are the bit-exact path.
 //
 // Hazards the barriers cover: (1) between stages (threads exchange amplitudes through the tile
-// buffer); (2) before the next tile's loads overwrite the buffer (after the last stage's loads);
-// (3) between a stage's loads and stores when the stage holds a lazy x, because threads then store
-// into EACH OTHER's slots (TStage::sync_after_load); (4) across GPUs, dist_barrier() kernels
-// around every pass that touches a peer shard, plus a system fence after the peer stores.
+// buffer); (2) before the next tile's load overwrites the buffer (after the last stage's loads);
+// (3) between a stage's loads and stores when the stage holds a lazy x on a thread bit, because
+// threads then store into EACH OTHER's slots (TStage::sync_after_load); (4) across GPUs,
+// dist_barrier() kernels around every pass that touches a peer shard, plus a system fence after
+// the peer stores.
+#include <mutex>
+
 #include "engine.h"
 #include "gates.cuh"
 
@@ -53,16 +63,10 @@ namespace qv {
 constexpr int NV = TILE_NV;
 constexpr int TR = TILE_R;
 
-__device__ __forceinline__ uint32_t swz(uint32_t j) {
-    return j ^ (((j >> 3) ^ (j >> 6) ^ (j >> 9)) & 7u);
-}
+// tile-local index -> 16-byte slot of the padded-linear tile buffer
+__device__ __forceinline__ uint32_t slot16(uint32_t j, uint32_t L) { return j + (j >> L); }
 
-__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-
-// ---- op bodies: templated on kind and register slot(s), fully unrolled over the 16 slots -----
+// ---- op bodies of the FULL interpreter: templated on kind and register slot(s) ------------------
 #define QV_FOR_K _Pragma("unroll") for (int K = 0; K < NV; ++K)
 // Controls held in register slots are warp-uniform (okmask comes from the op descriptor): keep
 // them as real branches -- the empty volatile asm stops the compiler from if-converting the
@@ -196,28 +200,24 @@ __device__ __forceinline__ void body_diag(amp (&v)[NV], const GP &g, const uint3
     case MC_DU + k5: body_diag<KIND, false, ALL>(v, g, ok, __popc(grp & m.a_thr) + (fl & 7u), 0); break; \
     case MC_DG + k5: body_diag<KIND, true, ALL>(v, g, ok, __popc(grp & m.a_thr) + (fl & 7u), m.a_reg & 0xFFFFu); break;
 
-// ALL: no control sits in a register slot (okmask = 0xFFFF) -- the common case runs without
-// any per-slot predicate.
-// One decoded op: the 32-byte MOp as it sits in shared memory (two 16-byte loads).
+// One decoded op of the FULL interpreter: the first 32 bytes of the MOp (two 16-byte loads).
 struct MDec {
     uint32_t w0;        // code | dagger << 8 | okmask << 16
     uint32_t ctrl_thr;
     uint32_t a_thr;
-    uint32_t a_reg;     // low 16 bits
+    uint32_t a_reg;     // low 16 bits (high 16: the op's index)
     double ph_re, ph_im;
 };
 
-// FULL: the interpreter carries the arms of every kind.  Passes made only of the common kinds
-// (diagonal class, x, y, rx, ry, h1) run the lean instance instead: the rare arms (u1/u2 keep a
-// whole matrix live, the two-bit ops have the most temporaries) set the register pressure of the
-// whole op loop, and without them its loop state stays in registers.
-template <bool ALL, bool FULL>
+// ALL: no control sits in a register slot (okmask = 0xFFFF) -- the common case runs without
+// any per-slot predicate.
+template <bool ALL>
 __device__ __forceinline__ void apply_mop(const MDec &m, const uint32_t fl, const uint32_t grp,
                                           const amp *__restrict__ mats, amp (&v)[NV]) {
     GP g;
     g.c = m.ph_re;
     g.s = m.ph_im;
-    g.dagger = (m.w0 >> 8) & 0xFFu;
+    g.dagger = (m.w0 >> 8) & 1u;
     g.ybase = ~2u;                      // y on ONE bit (the planner splits multi-bit x/y masks)
     g.mat = mats + m.a_thr;             // u1/u2 only
     const uint32_t ok = m.w0 >> 16;
@@ -236,7 +236,6 @@ __device__ __forceinline__ void apply_mop(const MDec &m, const uint32_t fl, cons
     QV_P1(QVNT_H1, MC_P1 + 16)
     default: break;
     }
-    if (!FULL) return;
     switch (code) {
     QV_P1(QVNT_U1, MC_P1 + 20)
     QV_P2X(QVNT_RXX, MC_P2X + 0)
@@ -257,41 +256,36 @@ __device__ __forceinline__ void apply_mop(const MDec &m, const uint32_t fl, cons
 
 // ---- stage plumbing shared by both interpreters ------------------------------------------------
 // A stage gives the thread of group `grp` the 16 amplitudes whose tile-local indices are
-// jl ^ (subset of the 4 register-slot bits).  All shared-memory addresses are 32-bit
-// shared-window offsets, XOR-swizzled (swz is GF(2)-linear: address(K) = mine_o ^ c[..]).
+// jl | (subset of the 4 register-slot bits).  All shared-memory addresses are 32-bit
+// shared-window byte offsets into the padded-linear tile buffer: address(K) = mine_o + sum of c[j]
+// over K's slot bits.
 struct StageCtx {
     uint32_t r_lpos;    // 4 bytes: register slot j -> tile-local bit position
-    uint32_t c[TR];     // swizzled byte offsets of the 4 register-slot bits
+    uint32_t c[TR];     // byte offsets of the 4 register-slot bits
     uint32_t jl;        // tile-local index of slot pattern 0
-    uint32_t mine_o;    // its swizzled byte offset
+    uint32_t mine_o;    // its byte offset
     unsigned long long goff;   // last stage, local tiles: byte offset of jl inside the tile's span of the shard
 };
 
 // Per-(stage, thread) constants are computed ONCE per kernel (every tile of the pass runs the same
-// stages) and kept in shared memory: word = (16 * swz(jl)) << 16 | jl.
-__device__ __forceinline__ uint32_t stage_jl(const uint32_t stage_s, const uint32_t n_t, const uint32_t grp) {
-    uint32_t sw[8];      // the TStage: op_begin, op_end, r_lpos[4], t_lpos[16], pad
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
-                 : "=r"(sw[0]), "=r"(sw[1]), "=r"(sw[2]), "=r"(sw[3]) : "r"(stage_s) : "memory");
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
-                 : "=r"(sw[4]), "=r"(sw[5]), "=r"(sw[6]), "=r"(sw[7]) : "r"(stage_s + 16u) : "memory");
+// stages) and kept in shared memory: word = slot16(jl) << 16 | jl.
+__device__ __forceinline__ uint32_t stage_jl(const TStage &st, const uint32_t n_t, const uint32_t grp) {
     uint32_t jl = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < 16; ++k) {
-        if (k < n_t) jl |= ((grp >> k) & 1u) << ((sw[3 + (k >> 2)] >> (8 * (k & 3))) & 0xFFu);
-    }
+    for (uint32_t k = 0; k < n_t; ++k) jl |= ((grp >> k) & 1u) << st.t_lpos[k];
     return jl;
 }
 
-__device__ __forceinline__ StageCtx stage_ctx(const uint32_t stage_s, const uint32_t jltab_s, const uint32_t ctab_s) {
+__device__ __forceinline__ StageCtx stage_ctx(const TStage *st, const uint32_t *jlw, const uint4 *ctab) {
     StageCtx x;
-    uint32_t w;
-    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(x.r_lpos) : "r"(stage_s + 8u) : "memory");
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
-                 : "=r"(x.c[0]), "=r"(x.c[1]), "=r"(x.c[2]), "=r"(x.c[3]) : "r"(ctab_s) : "memory");
-    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(w) : "r"(jltab_s) : "memory");
+    x.r_lpos = *reinterpret_cast<const uint32_t *>(st->r_lpos);
+    const uint4 c = *ctab;
+    x.c[0] = c.x;
+    x.c[1] = c.y;
+    x.c[2] = c.z;
+    x.c[3] = c.w;
+    const uint32_t w = *jlw;
     x.jl = w & 0xFFFFu;
-    x.mine_o = w >> 16;
+    x.mine_o = (w >> 16) * 16u;
     x.goff = 0;
     return x;
 }
@@ -299,24 +293,41 @@ __device__ __forceinline__ StageCtx stage_ctx(const uint32_t stage_s, const uint
 __device__ __forceinline__ void stage_load(const uint32_t tile_s, const StageCtx &x, amp (&v)[NV]) {
 #pragma unroll
     for (int K = 0; K < NV; ++K) {
-        uint32_t a = x.mine_o;
-        if (K & 1) a ^= x.c[0];
-        if (K & 2) a ^= x.c[1];
-        if (K & 4) a ^= x.c[2];
-        if (K & 8) a ^= x.c[3];
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v[K].x), "=d"(v[K].y) : "r"(tile_s + a) : "memory");
+        uint32_t a = tile_s + x.mine_o;
+        if (K & 1) a += x.c[0];
+        if (K & 2) a += x.c[1];
+        if (K & 4) a += x.c[2];
+        if (K & 8) a += x.c[3];
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v[K].x), "=d"(v[K].y) : "r"(a) : "memory");
     }
 }
 
-__device__ __forceinline__ void stage_store_smem(const uint32_t tile_s, const StageCtx &x, const amp (&v)[NV]) {
+// After lazy inversions (FC_LI) register K of the thread holds the amplitude of slot pattern
+// K ^ ib (ib = the inverted slots).  Folded into the store addressing, which is additive in the
+// slot bits: base += step[j] and step[j] = -step[j] for every inverted slot j.  `inv` carries one
+// byte per slot (0 or MOP_ALT_BYTES).
+template <typename T>
+__device__ __forceinline__ void fold_inv(const uint32_t inv, T &base, T (&step)[TR]) {
+#pragma unroll
+    for (int j = 0; j < TR; ++j)
+        if ((inv >> (8 * j)) & 0xFFu) {
+            base += step[j];
+            step[j] = (T)0 - step[j];
+        }
+}
+
+__device__ __forceinline__ void stage_store_smem(const uint32_t tile_s, const StageCtx &x, const uint32_t inv,
+                                                 const amp (&v)[NV]) {
+    uint32_t base = tile_s + x.mine_o, c[TR] = {x.c[0], x.c[1], x.c[2], x.c[3]};
+    if (inv) fold_inv(inv, base, c);
 #pragma unroll
     for (int K = 0; K < NV; ++K) {
-        uint32_t a = x.mine_o;
-        if (K & 1) a ^= x.c[0];
-        if (K & 2) a ^= x.c[1];
-        if (K & 4) a ^= x.c[2];
-        if (K & 8) a ^= x.c[3];
-        asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(tile_s + a), "d"(v[K].x), "d"(v[K].y) : "memory");
+        uint32_t a = base;
+        if (K & 1) a += c[0];
+        if (K & 2) a += c[1];
+        if (K & 4) a += c[2];
+        if (K & 8) a += c[3];
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(a), "d"(v[K].x), "d"(v[K].y) : "memory");
     }
 }
 
@@ -326,7 +337,7 @@ __device__ __forceinline__ void stage_store_smem(const uint32_t tile_s, const St
 // register slots, so a warp's store instruction covers up to 512 contiguous bytes.
 __device__ __forceinline__ void stage_store_global(const uint32_t ptr0_s, const uint32_t L,
                                                    const unsigned long long toff, const StageCtx &x,
-                                                   const amp (&v)[NV]) {
+                                                   const uint32_t inv, const amp (&v)[NV]) {
     uint32_t offc[TR], chc[TR];       // per register slot: its bit inside the chunk / in the chunk index
 #pragma unroll
     for (int j = 0; j < TR; ++j) {
@@ -334,33 +345,35 @@ __device__ __forceinline__ void stage_store_global(const uint32_t ptr0_s, const 
         offc[j] = lp < L ? (16u << lp) : 0u;
         chc[j] = lp < L ? 0u : (8u << (lp - L));
     }
-    const unsigned long long off0 = toff + (x.jl & ((1u << L) - 1u)) * 16u;
-    const uint32_t ch0 = ptr0_s + (x.jl >> L) * 8u;
+    uint32_t off0 = (x.jl & ((1u << L) - 1u)) * 16u;
+    uint32_t ch0 = ptr0_s + (x.jl >> L) * 8u;
+    if (inv) {
+        fold_inv(inv, off0, offc);
+        fold_inv(inv, ch0, chc);
+    }
 #pragma unroll
     for (int K = 0; K < NV; ++K) {
-        uint32_t off = 0, ch = ch0;
-        if (K & 1) { off |= offc[0]; ch += chc[0]; }      // (ch is an address: add, the table is not
-        if (K & 2) { off |= offc[1]; ch += chc[1]; }      //  aligned to its own size)
-        if (K & 4) { off |= offc[2]; ch += chc[2]; }
-        if (K & 8) { off |= offc[3]; ch += chc[3]; }
+        uint32_t off = off0, ch = ch0;
+        if (K & 1) { off += offc[0]; ch += chc[0]; }
+        if (K & 2) { off += offc[1]; ch += chc[1]; }
+        if (K & 4) { off += offc[2]; ch += chc[2]; }
+        if (K & 8) { off += offc[3]; ch += chc[3]; }
         unsigned long long base;
         asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(base) : "r"(ch) : "memory");
-        *reinterpret_cast<amp *>(base + off0 + off) = v[K];
+        *reinterpret_cast<amp *>(base + toff + off) = v[K];
     }
 }
 
 // Same, for tiles that lie entirely in this GPU's shard: the address is affine in the index bits,
 // address(K) = base + goff(thread) + sum of the byte offsets of K's register-slot bits -- no table.
-__device__ __forceinline__ void stage_store_global_local(const unsigned long long base, const uint32_t gpos_s,
-                                                         const StageCtx &x, const amp (&v)[NV]) {
+__device__ __forceinline__ void stage_store_global_local(const unsigned long long base, const uint8_t *s_gpos,
+                                                         const StageCtx &x, const uint32_t inv,
+                                                         const amp (&v)[NV]) {
     unsigned long long g[TR];
 #pragma unroll
-    for (int j = 0; j < TR; ++j) {
-        uint32_t gp;
-        asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(gp) : "r"(gpos_s + ((x.r_lpos >> (8 * j)) & 0xFFu)) : "memory");
-        g[j] = 16ull << gp;
-    }
-    const unsigned long long a0 = base + x.goff;
+    for (int j = 0; j < TR; ++j) g[j] = 16ull << s_gpos[(x.r_lpos >> (8 * j)) & 0xFFu];
+    unsigned long long a0 = base + x.goff;
+    if (inv) fold_inv(inv, a0, g);
 #pragma unroll
     for (int K = 0; K < NV; ++K) {
         unsigned long long a = a0;
@@ -400,8 +413,8 @@ __device__ __forceinline__ void stage_ops_full(const uint32_t ops_s, const uint3
             if (o + 1 < oe) fetch(o + 1);
             continue;
         }
-        if ((m.w0 >> 16) == 0xFFFFu) apply_mop<true, true>(m, fl, grp, mats, v);
-        else apply_mop<false, true>(m, fl, grp, mats, v);
+        if ((m.w0 >> 16) == 0xFFFFu) apply_mop<true>(m, fl, grp, mats, v);
+        else apply_mop<false>(m, fl, grp, mats, v);
         if (o + 1 < oe) fetch(o + 1);
     }
 }
@@ -411,9 +424,11 @@ __device__ __forceinline__ void stage_ops_full(const uint32_t ops_s, const uint3
 // coefficient-driven forms of FCode (engine.h); every arm below updates the 16 register-resident
 // amplitudes IN PLACE through inline PTX whose operands are tied ("+d"), so each amplitude keeps
 // one home register through the whole op loop: no register shuffling at the merge points of the
-// dispatch, no selects -- per op the instruction stream is the FP64 arithmetic plus ~15
-// instructions of fetch / test / dispatch.  4 FP64 instructions per amplitude and op
-// (2 mul + 2 fma), the same count as the reference formulas with contraction.
+// dispatch, no selects.  Per op the instruction stream is the FP64 arithmetic (4 per amplitude:
+// 2 mul + 2 fma, the same count as the reference formulas with contraction) plus one 16-byte
+// header load, one test of the header's flag bits, the jump table and two 16-byte coefficient
+// loads inside the arm.  x / cx never move data unless the control itself sits in a register slot:
+// they flip a bit of the thread's store index (FC_LX) or mark a register slot as inverted (FC_LI).
 // ================================================================================================
 __device__ __forceinline__ void f_pair_real(amp &p0, amp &p1, double a, double b, double c, double d) {
     asm volatile("{\n\t.reg .f64 t, u, w, z;\n\t"
@@ -428,34 +443,21 @@ __device__ __forceinline__ void f_pair_real(amp &p0, amp &p1, double a, double b
                  : "+d"(p0.x), "+d"(p0.y), "+d"(p1.x), "+d"(p1.y)
                  : "d"(a), "d"(b), "d"(c), "d"(d));
 }
-// new0 = (p0 + p1) * s ; new1 = (p0 - p1) * s
-__device__ __forceinline__ void f_pair_addsub(amp &p0, amp &p1, double sc) {
-    asm volatile("{\n\t.reg .f64 t, u, w, z;\n\t"
-                 "add.rn.f64 t, %0, %2;\n\t"
-                 "sub.rn.f64 u, %0, %2;\n\t"
-                 "add.rn.f64 w, %1, %3;\n\t"
-                 "sub.rn.f64 z, %1, %3;\n\t"
-                 "mul.rn.f64 %0, t, %4;\n\t"
-                 "mul.rn.f64 %2, u, %4;\n\t"
-                 "mul.rn.f64 %1, w, %4;\n\t"
-                 "mul.rn.f64 %3, z, %4;\n\t}"
-                 : "+d"(p0.x), "+d"(p0.y), "+d"(p1.x), "+d"(p1.y)
-                 : "d"(sc));
-}
-// new0 = a*p0 - i*b*p1 ; new1 = -i*c*p0 + d*p1   (nb = -b, nc = -c)
-__device__ __forceinline__ void f_pair_cross(amp &p0, amp &p1, double a, double b, double nb, double c, double nc,
-                                             double d) {
-    asm volatile("{\n\t.reg .f64 t, u, w, z;\n\t"
+// new0 = a*p0 - i*b*p1 ; new1 = -i*c*p0 + d*p1
+__device__ __forceinline__ void f_pair_cross(amp &p0, amp &p1, double a, double b, double c, double d) {
+    asm volatile("{\n\t.reg .f64 t, u, w, z, nb, nc;\n\t"
+                 "neg.f64 nb, %5;\n\t"
+                 "neg.f64 nc, %6;\n\t"
                  "mul.rn.f64 t, %4, %0;\n\t"      // a * p0.x
                  "mul.rn.f64 w, %4, %1;\n\t"      // a * p0.y
-                 "mul.rn.f64 u, %7, %1;\n\t"      // c * p0.y
-                 "mul.rn.f64 z, %8, %0;\n\t"      // -c * p0.x
+                 "mul.rn.f64 u, %6, %1;\n\t"      // c * p0.y
+                 "mul.rn.f64 z, nc, %0;\n\t"      // -c * p0.x
                  "fma.rn.f64 %0, %5, %3, t;\n\t"  // p0.x = b * p1.y + a * p0.x
-                 "fma.rn.f64 %1, %6, %2, w;\n\t"  // p0.y = -b * p1.x + a * p0.y
-                 "fma.rn.f64 %2, %9, %2, u;\n\t"  // p1.x = d * p1.x + c * p0.y
-                 "fma.rn.f64 %3, %9, %3, z;\n\t}" // p1.y = d * p1.y - c * p0.x
+                 "fma.rn.f64 %1, nb, %2, w;\n\t"  // p0.y = -b * p1.x + a * p0.y
+                 "fma.rn.f64 %2, %7, %2, u;\n\t"  // p1.x = d * p1.x + c * p0.y
+                 "fma.rn.f64 %3, %7, %3, z;\n\t}" // p1.y = d * p1.y - c * p0.x
                  : "+d"(p0.x), "+d"(p0.y), "+d"(p1.x), "+d"(p1.y)
-                 : "d"(a), "d"(b), "d"(nb), "d"(c), "d"(nc), "d"(d));
+                 : "d"(a), "d"(b), "d"(c), "d"(d));
 }
 __device__ __forceinline__ void f_swap(amp &p0, amp &p1) {
     asm volatile("{\n\t.reg .f64 t, u;\n\t"
@@ -467,92 +469,102 @@ __device__ __forceinline__ void f_swap(amp &p0, amp &p1) {
                  "mov.f64 %3, u;\n\t}"
                  : "+d"(p0.x), "+d"(p0.y), "+d"(p1.x), "+d"(p1.y));
 }
-// p *= (fr, fi)   (nfi = -fi)
-__device__ __forceinline__ void f_cmul(amp &p, double fr, double fi, double nfi) {
-    asm volatile("{\n\t.reg .f64 t, u;\n\t"
-                 "mul.rn.f64 t, %4, %1;\n\t"      // -fi * y
+// p *= (fr, fi)
+__device__ __forceinline__ void f_cmul(amp &p, double fr, double fi) {
+    asm volatile("{\n\t.reg .f64 t, u, nfi;\n\t"
+                 "neg.f64 nfi, %3;\n\t"
+                 "mul.rn.f64 t, nfi, %1;\n\t"     // -fi * y
                  "mul.rn.f64 u, %3, %0;\n\t"      //  fi * x
                  "fma.rn.f64 %0, %2, %0, t;\n\t"  // x = fr * x - fi * y
                  "fma.rn.f64 %1, %2, %1, u;\n\t}" // y = fr * y + fi * x
                  : "+d"(p.x), "+d"(p.y)
-                 : "d"(fr), "d"(fi), "d"(nfi));
+                 : "d"(fr), "d"(fi));
 }
 
-struct FDec {
-    uint32_t w0;        // code | flags << 8 | okmask << 16
-    uint32_t ctrl_thr;
-    uint32_t a_thr;
-    uint32_t a_reg;     // low 16 bits
-    double c0, c1, c2, c3;
-};
+// controls held in register slots while slots are inverted: register K holds slot pattern K ^ ib,
+// so its predicate is okmask bit K ^ ib
+__device__ __forceinline__ uint32_t perm_ok(uint32_t ok, const uint32_t inv) {
+    if (inv & 0x000000FFu) ok = ((ok & 0x5555u) << 1) | ((ok >> 1) & 0x5555u);
+    if (inv & 0x0000FF00u) ok = ((ok & 0x3333u) << 2) | ((ok >> 2) & 0x3333u);
+    if (inv & 0x00FF0000u) ok = ((ok & 0x0F0Fu) << 4) | ((ok >> 4) & 0x0F0Fu);
+    if (inv & 0xFF000000u) ok = ((ok & 0x00FFu) << 8) | ((ok >> 8) & 0x00FFu);
+    return ok;
+}
+
+// the op's coefficient block: 32 bytes at +16, or the `alt` block behind it while slot RB is inverted
+struct C4 { double c0, c1, c2, c3; };
+__device__ __forceinline__ C4 coef4(const unsigned char *op, const uint32_t blk) {
+    const double2 *c = reinterpret_cast<const double2 *>(op + 16u + blk);
+    const double2 a = c[0], b = c[1];
+    return {a.x, a.y, b.x, b.y};
+}
 
 template <int RB, bool ALL>
-__device__ __forceinline__ void farm_pr(amp (&v)[NV], const FDec &m, const uint32_t ok) {
+__device__ __forceinline__ void farm_pr(amp (&v)[NV], const unsigned char *op, const uint32_t inv, const uint32_t ok) {
+    const C4 m = coef4(op, (inv >> (8 * RB)) & 0xFFu);
     QV_FOR_K {
         if (K & (1 << RB)) continue;
         if (ALL || ((ok >> K) & 1u)) f_pair_real(v[K], v[K | (1 << RB)], m.c0, m.c1, m.c2, m.c3);
     }
 }
 template <int RB, bool ALL>
-__device__ __forceinline__ void farm_pa(amp (&v)[NV], const FDec &m, const uint32_t ok) {
+__device__ __forceinline__ void farm_px(amp (&v)[NV], const unsigned char *op, const uint32_t inv, const uint32_t ok) {
+    const C4 m = coef4(op, (inv >> (8 * RB)) & 0xFFu);
     QV_FOR_K {
         if (K & (1 << RB)) continue;
-        if (ALL || ((ok >> K) & 1u)) f_pair_addsub(v[K], v[K | (1 << RB)], m.c0);
+        if (ALL || ((ok >> K) & 1u)) f_pair_cross(v[K], v[K | (1 << RB)], m.c0, m.c1, m.c2, m.c3);
     }
 }
-template <int RB, bool ALL>
-__device__ __forceinline__ void farm_px(amp (&v)[NV], const FDec &m, const uint32_t ok) {
-    const double nb = -m.c1, nc = -m.c2;
-    QV_FOR_K {
-        if (K & (1 << RB)) continue;
-        if (ALL || ((ok >> K) & 1u)) f_pair_cross(v[K], v[K | (1 << RB)], m.c0, m.c1, nb, m.c2, nc, m.c3);
-    }
-}
-template <int RB, bool ALL>
+template <int RB>
 __device__ __forceinline__ void farm_sw(amp (&v)[NV], const uint32_t ok) {
     QV_FOR_K {
         if (K & (1 << RB)) continue;
-        if (ALL || ((ok >> K) & 1u)) f_swap(v[K], v[K | (1 << RB)]);
+        if ((ok >> K) & 1u) f_swap(v[K], v[K | (1 << RB)]);
     }
 }
 // diagonal, no target bit in a register slot: one factor for the whole thread
 template <bool ALL>
-__device__ __forceinline__ void farm_du(amp (&v)[NV], const FDec &m, const uint32_t ok, const uint32_t par) {
-    if (!par && (m.w0 & ((uint32_t)MOP_SKIP0 << 8))) return;
-    const double fr = par ? m.c2 : m.c0, fi = par ? m.c3 : m.c1, nfi = -fi;
+__device__ __forceinline__ void farm_du(amp (&v)[NV], const unsigned char *op, const uint32_t w0, const uint32_t ok,
+                                        const uint32_t par) {
+    if (!par && (w0 & ((uint32_t)MOP_SKIP0 << 8))) return;
+    const double2 f = *reinterpret_cast<const double2 *>(op + 16u + 16u * par);
     QV_FOR_K {
-        if (ALL || ((ok >> K) & 1u)) f_cmul(v[K], fr, fi, nfi);
+        if (ALL || ((ok >> K) & 1u)) f_cmul(v[K], f.x, f.y);
     }
 }
-// diagonal, exactly one target bit in register slot RB (+ parity `par` of the target bits elsewhere)
+// diagonal, exactly one target bit in register slot RB (+ parity `par` of the target bits elsewhere):
+// the slot's inversion and the outer parity both exchange the roles of f0 and f1 -- which is what
+// the `alt` block holds
 template <int RB, bool ALL>
-__device__ __forceinline__ void farm_ds(amp (&v)[NV], const FDec &m, const uint32_t ok, const uint32_t par) {
-    double f0r = m.c0, f0i = m.c1, f1r = m.c2, f1i = m.c3;
-    bool skip0 = (m.w0 & ((uint32_t)MOP_SKIP0 << 8)) != 0;
-    if (par) {                    // rzz with its second bit outside the slots: the roles swap
-        f0r = m.c2; f0i = m.c3; f1r = m.c0; f1i = m.c1;
-        skip0 = false;
-    }
-    const double n0 = -f0i, n1 = -f1i;
-    if (!skip0) {
+__device__ __forceinline__ void farm_ds(amp (&v)[NV], const unsigned char *op, const uint32_t w0, const uint32_t inv,
+                                        const uint32_t ok, const uint32_t par) {
+    const uint32_t blk = ((inv >> (8 * RB)) & 0xFFu) ^ (par * MOP_ALT_BYTES);
+    const C4 m = coef4(op, blk);
+    const bool skip0 = (w0 & ((uint32_t)MOP_SKIP0 << 8)) != 0;      // the ORIGINAL f0 is 1
+    if (!skip0 || blk != 0u) {
         QV_FOR_K {
             if (K & (1 << RB)) continue;
-            if (ALL || ((ok >> K) & 1u)) f_cmul(v[K], f0r, f0i, n0);
+            if (ALL || ((ok >> K) & 1u)) f_cmul(v[K], m.c0, m.c1);
         }
     }
-    QV_FOR_K {
-        if (!(K & (1 << RB))) continue;
-        if (ALL || ((ok >> K) & 1u)) f_cmul(v[K], f1r, f1i, n1);
+    if (!skip0 || blk == 0u) {
+        QV_FOR_K {
+            if (!(K & (1 << RB))) continue;
+            if (ALL || ((ok >> K) & 1u)) f_cmul(v[K], m.c2, m.c3);
+        }
     }
 }
 // diagonal, any set of target bits in register slots (rare: rzz with both bits in slots)
-__device__ __forceinline__ void farm_dg(amp (&v)[NV], const FDec &m, const uint32_t ok, const uint32_t par) {
-    const uint32_t a_reg = m.a_reg & 0xFu;
-    const double n0 = -m.c1, n1 = -m.c3;
+__device__ __forceinline__ void farm_dg(amp (&v)[NV], const unsigned char *op, const uint32_t a_reg, const uint32_t inv,
+                                        const uint32_t ok, uint32_t par) {
+    const C4 m = coef4(op, 0u);
+    // register K holds slot pattern K ^ ib: the inverted target slots add their parity
+    const uint32_t ib = ((inv >> 5) & 1u) | ((inv >> 12) & 2u) | ((inv >> 19) & 4u) | ((inv >> 26) & 8u);
+    par = (par + __popc(ib & a_reg)) & 1u;
     QV_FOR_K {
         if ((ok >> K) & 1u) {
-            if ((__popc((uint32_t)K & a_reg) + par) & 1u) f_cmul(v[K], m.c2, m.c3, n1);
-            else f_cmul(v[K], m.c0, m.c1, n0);
+            if ((__popc((uint32_t)K & a_reg) + par) & 1u) f_cmul(v[K], m.c2, m.c3);
+            else f_cmul(v[K], m.c0, m.c1);
         }
     }
 }
@@ -563,107 +575,124 @@ __device__ __forceinline__ void farm_dg(amp (&v)[NV], const FDec &m, const uint3
     case base + 2: ARM<2, ALLV>(__VA_ARGS__); break;                   \
     case base + 3: ARM<3, ALLV>(__VA_ARGS__); break;
 
-// One jump table over (form, slot, "no control sits in a register slot"): the planner adds
-// FC_ALL to the code when okmask == 0xFFFF, so the common case runs without per-slot predicates.
-__device__ __forceinline__ void apply_fop(const FDec &m, const uint32_t fl, const uint32_t grp, amp (&v)[NV]) {
-    const uint32_t ok = m.w0 >> 16;
-    uint32_t code = m.w0 & 0xFFu;
-    asm volatile("" : "+r"(code));
-    switch (code) {
-#ifndef QV_EXP_SMALL
-    QV_F4(farm_pr, false, FC_PR, v, m, ok)
-    QV_F4(farm_px, false, FC_PX, v, m, ok)
-#endif
-    QV_F4(farm_sw, false, FC_SW, v, ok)
-#ifndef QV_EXP_SMALL
-    case FC_DU: farm_du<false>(v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u); break;
-    QV_F4(farm_ds, false, FC_DS, v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u)
-    case FC_DG: farm_dg(v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u); break;
-    QV_F4(farm_pa, false, FC_PA, v, m, ok)
-#endif
-    QV_F4(farm_pr, true, FC_ALL + FC_PR, v, m, ok)
-    QV_F4(farm_px, true, FC_ALL + FC_PX, v, m, ok)
-    QV_F4(farm_sw, true, FC_ALL + FC_SW, v, ok)
-    case FC_ALL + FC_DU: farm_du<true>(v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u); break;
-    QV_F4(farm_ds, true, FC_ALL + FC_DS, v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u)
-    case FC_ALL + FC_DG: farm_dg(v, m, ok, (__popc(grp & m.a_thr) + fl) & 1u); break;
-    QV_F4(farm_pa, true, FC_ALL + FC_PA, v, m, ok)
-    default: break;
-    }
-}
-
 // The op loop of the FAST interpreter.
-// FC_LX ("lazy x"): an x whose target and controls all sit on thread / outer bits is a permutation
-// BETWEEN threads: it costs three XORs -- the thread flips the bit in the index it will store its
-// amplitudes to (x.jl / x.mine_o) and in the virtual group number `vgrp` the later ops of the
-// stage test their thread-bit controls and parities against.
-__device__ __forceinline__ void stage_ops_fast(const uint32_t ops_s, const uint32_t flags_s, const uint32_t ob,
-                                               const uint32_t oe, const uint32_t grp, StageCtx &x, amp (&v)[NV]) {
+__device__ __forceinline__ void stage_ops_fast(const unsigned char *ops, const volatile uint8_t *flags, const uint32_t ob,
+                                               const uint32_t oe, const uint32_t grp, const uint32_t L, StageCtx &x,
+                                               uint32_t &inv, amp (&v)[NV]) {
     uint32_t vgrp = grp;
-    for (uint32_t o = ob; o < oe; ++o) {
-        const uint32_t op_a = ops_s + MOP_BYTES * o;
-        uint32_t fl;
-        FDec m;
-        asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(fl) : "r"(flags_s + o) : "memory");
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
-                     : "=r"(m.w0), "=r"(m.ctrl_thr), "=r"(m.a_thr), "=r"(m.a_reg)
-                     : "r"(op_a)
-                     : "memory");
-        if (!(fl & 0x80u) || (~vgrp & m.ctrl_thr)) {
-            if ((m.w0 & 0xFFu) == (uint32_t)FC_DM) o += m.a_reg & 0xFFFFu;     // the whole run shares the controls
-            continue;
+    const unsigned char *p = ops + MOP_BYTES * ob;
+    const unsigned char *const pe = ops + MOP_BYTES * oe;
+    while (p != pe) {
+        const unsigned char *const op = p;
+        const uint4 h = *reinterpret_cast<const uint4 *>(op);     // w0 | ctrl_thr | a_thr | a_reg + idx << 16
+        p += MOP_BYTES;
+        uint32_t code = h.x & 0xFFu;
+        if (h.x & ((uint32_t)MOP_COND << 8)) {
+            bool skip = (~vgrp & h.y) != 0u;
+            if (h.x & ((uint32_t)MOP_CONDB << 8)) skip = skip || !(flags[h.w >> 16] & 0x80u);
+            if (skip) {
+                if (code == (uint32_t)FC_DM || code == (uint32_t)(FC_DM + FC_MASKED)) p += MOP_BYTES * (h.w & 0xFFFFu);
+                continue;
+            }
         }
-        if ((m.w0 & 0xFFu) == (uint32_t)FC_DM) {
+        // parity of the diagonal target bits on thread bits and outside the tile
+        auto dpar = [&](const uint32_t w0, const uint32_t a_thr, const uint32_t idx) -> uint32_t {
+            uint32_t c = (uint32_t)__popc(vgrp & a_thr);
+            if (w0 & ((uint32_t)MOP_PARB << 8)) c += flags[idx];
+            return c & 1u;
+        };
+        uint32_t ok = h.x >> 16;
+        if (code >= (uint32_t)FC_MASKED && inv != 0u) ok = perm_ok(ok, inv);
+        asm volatile("" : "+r"(code));      // keep the dispatch value 32-bit: one jump table (BRX)
+        switch (code) {
+        QV_F4(farm_pr, true, FC_PR, v, op, inv, ok)
+        QV_F4(farm_px, true, FC_PX, v, op, inv, ok)
+        QV_F4(farm_ds, true, FC_DS, v, op, h.x, inv, ok, dpar(h.x, h.z, h.w >> 16))
+        case FC_DU: farm_du<true>(v, op, h.x, ok, dpar(h.x, h.z, h.w >> 16)); break;
+        case FC_DG:
+        case FC_DG + FC_MASKED: farm_dg(v, op, h.w & 0xFu, inv, ok, dpar(h.x, h.z, h.w >> 16)); break;
+        case FC_LX: {
+            // x between threads: the thread will store its amplitudes where the partner's were
+            const uint32_t lp = h.w & 0xFFu, bit = 1u << lp, d = 16u * slot16(bit, L);
+            vgrp ^= h.z;
+            x.mine_o += (x.jl & bit) ? 0u - d : d;
+            x.jl ^= bit;
+            x.goff ^= 16ull << ((h.w >> 8) & 0xFFu);
+            break;
+        }
+        case FC_LI: inv ^= MOP_ALT_BYTES << (8u * (h.w & 3u)); break;       // (a_reg = the slot)
+        case FC_DM:
+        case FC_DM + FC_MASKED: {
             // merged diagonal run: acc = product of the constituents' factors for this thread
-            const uint32_t cnt = m.a_reg & 0xFFFFu;
+            const uint32_t cnt = h.w & 0xFFFFu;
             double ar = 1.0, ai = 0.0;
-            for (uint32_t k = 1; k <= cnt; ++k) {
-                const uint32_t a2 = op_a + MOP_BYTES * k;
-                uint32_t fl2, w2, athr2;
-                asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(fl2) : "r"(flags_s + o + k) : "memory");
-                asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(w2) : "r"(a2) : "memory");
-                asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(athr2) : "r"(a2 + 8u) : "memory");
-                const uint32_t par = (__popc(vgrp & athr2) + fl2) & 1u;
-                if (!par && (w2 & ((uint32_t)MOP_SKIP0 << 8))) continue;
-                double fr, fi;
-                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(fr), "=d"(fi) : "r"(a2 + 16u + 16u * par) : "memory");
-                const double t = ar * fr - ai * fi;
-                ai = ar * fi + ai * fr;
+            for (uint32_t k = 0; k < cnt; ++k, p += MOP_BYTES) {
+                const uint4 h2 = *reinterpret_cast<const uint4 *>(p);
+                const uint32_t par = dpar(h2.x, h2.z, h2.w >> 16);
+                if (!par && (h2.x & ((uint32_t)MOP_SKIP0 << 8))) continue;
+                const double2 f = *reinterpret_cast<const double2 *>(p + 16u + 16u * par);
+                const double t = ar * f.x - ai * f.y;
+                ai = ar * f.y + ai * f.x;
                 ar = t;
             }
-            const uint32_t ok = m.w0 >> 16;
-            const double nai = -ai;
             QV_FOR_K {
-                if ((ok >> K) & 1u) f_cmul(v[K], ar, ai, nai);
+                if ((ok >> K) & 1u) f_cmul(v[K], ar, ai);
             }
-            o += cnt;
-            continue;
+            break;
         }
-        if ((m.w0 & 0xFFu) == (uint32_t)FC_LX) {
-            vgrp ^= m.a_thr;
-            x.jl ^= 1u << (m.a_reg & 0xFFu);
-            x.mine_o ^= 16u * swz(1u << (m.a_reg & 0xFFu));
-            x.goff ^= 16ull << (m.a_reg >> 8);           // (a_reg high byte: the bit's position in the shard)
-            continue;
+        QV_F4(farm_pr, false, FC_MASKED + FC_PR, v, op, inv, ok)
+        QV_F4(farm_px, false, FC_MASKED + FC_PX, v, op, inv, ok)
+        QV_F4(farm_ds, false, FC_MASKED + FC_DS, v, op, h.x, inv, ok, dpar(h.x, h.z, h.w >> 16))
+        case FC_MASKED + FC_DU: farm_du<false>(v, op, h.x, ok, dpar(h.x, h.z, h.w >> 16)); break;
+        case FC_SW + 0: farm_sw<0>(v, ok); break;
+        case FC_SW + 1: farm_sw<1>(v, ok); break;
+        case FC_SW + 2: farm_sw<2>(v, ok); break;
+        case FC_SW + 3: farm_sw<3>(v, ok); break;
+        default: break;
         }
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(m.c0), "=d"(m.c1) : "r"(op_a + 16u) : "memory");
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(m.c2), "=d"(m.c3) : "r"(op_a + 32u) : "memory");
-        apply_fop(m, fl, vgrp, v);
     }
 }
 
-// Kernel configurations: <threads per CTA, min CTAs per SM, tile buffers>.
-//   T == 12: 256 threads, 2 CTAs/SM, one 64 KiB buffer.  The last stage stores its registers
-//            straight to HBM, so the buffer is free as soon as that stage has read it: the next
-//            tile's cp.async loads are issued right there and overlap the last stage's arithmetic
-//            and stores.
-//   T <= 11: 128 threads, 4 CTAs/SM, one 32 KiB buffer each (default): the kernel is bound by
-//            instruction issue and latency, not by HBM, so the extra resident warps pay more
-//            than a second buffer does (option "tile_nbuf" = 2: 3 CTAs/SM with two buffers).
+// ---- TMA bulk copy + mbarrier (tile loads) -------------------------------------------------------
+__device__ __forceinline__ void mbar_init(const uint32_t mbar, const uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(const uint32_t mbar, const uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(const uint32_t mbar, const uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(mbar), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(const uint32_t dst, const unsigned long long src, const uint32_t bytes,
+                                         const uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+
+__device__ __forceinline__ void bulk_prefetch_l2(const unsigned long long src, const uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// Kernel configurations: <threads per CTA, min CTAs per SM>.
+//   T == 12: 256 threads, 2 CTAs/SM, one 68 KiB buffer.
+//   T <= 11: 128 threads, 4 CTAs/SM, one 34 KiB buffer each (default; option "tile_ctas" 3 / 5).
+// One buffer per CTA: the last stage stores its registers straight to HBM, so the buffer is free
+// as soon as that stage has read it -- the next tile's load is issued right there and overlaps
+// the last stage's arithmetic and stores.
 constexpr uint32_t META_SLOTS = 3;      // per-tile op flags rotate through 3 slots: preparing tile i+1 must not
                                         // race with the threads still running the ops of tile i-1
 
-template <int THREADS, int MINB, int NB, bool FULL>
+template <int THREADS, int MINB, bool FULL, bool BULK>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr hdr,
             const TStage *__restrict__ g_stages, const MOp *__restrict__ g_ops,
@@ -673,25 +702,28 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     const uint32_t T = hdr.T, L = hdr.L;
     const uint32_t n_ops = hdr.n_ops, n_stages = hdr.n_stages;
     const uint32_t tile_len = 1u << T;
-    const uint32_t tile_bytes = 16u << T;
     const uint32_t lmask = (1u << L) - 1u;
     const uint32_t n_chunks = 1u << (T - L);
+    const uint32_t chunk_bytes = 16u << L, chunk_stride = chunk_bytes + 16u;
+    const uint32_t buf_bytes = n_chunks * chunk_stride;
     const uint32_t flags_stride = (n_ops + 15u) & ~15u;
 
     // shared memory carve-up (16-byte aligned sections first)
-    unsigned char *tiles_b = smem_raw;                                            // NB * (16 << T)
-    MOp *s_ops = reinterpret_cast<MOp *>(smem_raw + (size_t)NB * tile_bytes);      // 48 * n_ops
+    unsigned char *tile_b = smem_raw;                                              // n_chunks * (16 * 2^L + 16)
+    unsigned long long *s_mbar = reinterpret_cast<unsigned long long *>(smem_raw + buf_bytes);   // 16
+    MOp *s_ops = reinterpret_cast<MOp *>(smem_raw + buf_bytes + 16u);              // 80 * n_ops
     TStage *s_stages = reinterpret_cast<TStage *>(s_ops + n_ops);                  // 32 * n_stages
     MBase *s_bases = reinterpret_cast<MBase *>(s_stages + n_stages);               // 16 * n_ops
     unsigned long long *s_ptr0 = reinterpret_cast<unsigned long long *>(s_bases + n_ops);   // 8 * n_chunks
     unsigned long long *s_goff = s_ptr0 + ((n_chunks + 1u) & ~1u);                 // 8 * nthr (last stage)
-    uint32_t *s_ctab = reinterpret_cast<uint32_t *>(s_goff + nthr);                // 16 * n_stages
-    uint32_t *s_jltab = s_ctab + 4u * n_stages;                                    // 4 * nthr * n_stages
+    uint4 *s_ctab = reinterpret_cast<uint4 *>(s_goff + nthr);                      // 16 * n_stages
+    uint32_t *s_jltab = reinterpret_cast<uint32_t *>(s_ctab + n_stages);           // 4 * nthr * n_stages
     uint8_t *s_gpos = reinterpret_cast<uint8_t *>(s_jltab + nthr * n_stages);      // 16
     uint8_t *s_flags_all = s_gpos + 16;                                            // 3 * flags_stride
 
     const uint32_t shard_shift = segs.shift;
     const uint64_t shard_mask = (1ull << shard_shift) - 1ull;
+    const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(s_mbar);
     // the pass program: same for every tile this CTA processes
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(g_ops + hdr.op_begin);
@@ -712,16 +744,17 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
                 if ((c >> j) & 1u) gidx |= 1ull << hdr.gpos[L + j];
             s_ptr0[c] = (unsigned long long)(uintptr_t)(segs.seg[gidx >> shard_shift] + (gidx & shard_mask));
         }
+        if (BULK && tid == 0) mbar_init(mbar, 1u);
     }
     const uint32_t n_t = T - TR;                     // thread bits per stage
     if (tid < 16u) s_gpos[tid] = hdr.gpos[tid];
     __syncthreads();                                 // the stage descriptors are in shared memory
     // per-(stage, thread) and per-stage constants, once per kernel
     for (uint32_t st = 0; st < n_stages; ++st) {
-        const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(s_stages + st);
-        const uint32_t jl = stage_jl(stage_s, n_t, tid);
-        s_jltab[st * nthr + tid] = ((16u * swz(jl)) << 16) | jl;
-        if (tid < (uint32_t)TR) s_ctab[4u * st + tid] = 16u * swz(1u << s_stages[st].r_lpos[tid]);
+        const uint32_t jl = stage_jl(s_stages[st], n_t, tid);
+        s_jltab[st * nthr + tid] = (slot16(jl, L) << 16) | jl;
+        if (tid < (uint32_t)TR)
+            reinterpret_cast<uint32_t *>(s_ctab + st)[tid] = 16u * slot16(1u << s_stages[st].r_lpos[tid], L);
         if (st + 1 == n_stages) {
             unsigned long long go = 0;
             for (uint32_t l = 0; l < T; ++l)
@@ -729,102 +762,120 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
             s_goff[tid] = go;
         }
     }
-    const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(tiles_b);
-    const uint32_t jltab_s = (uint32_t)__cvta_generic_to_shared(s_jltab);
-    const uint32_t ctab_s = (uint32_t)__cvta_generic_to_shared(s_ctab);
-    const uint32_t gpos_s = (uint32_t)__cvta_generic_to_shared(s_gpos);
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile_b);
     const unsigned long long shard_base = (unsigned long long)(uintptr_t)segs.seg[segs.rank];
     const uint32_t ops_s = (uint32_t)__cvta_generic_to_shared(s_ops);
-    const uint32_t stages_s = (uint32_t)__cvta_generic_to_shared(s_stages);
     const uint32_t flags_all_s = (uint32_t)__cvta_generic_to_shared(s_flags_all);
     const uint32_t ptr0_s = (uint32_t)__cvta_generic_to_shared(s_ptr0);
     const bool active = tid < (1u << n_t);           // this thread owns a group of 16 amplitudes
+    const bool need_flags = FULL || hdr.need_flags != 0u;
     __syncthreads();
 
-    // Metadata of the first tile >= t (stepping by the grid) that some op of this pass can change:
-    // per-op flags (bit 7: controls outside the tile satisfied; bits 0-2: popcount of the diagonal
-    // target mask over the bits outside the tile, mod 8) and the tile's byte offset inside the
-    // shard.  Tiles no op touches (multi-controlled gates) are skipped without being read.
-    // Returns n_tiles if there is none.
-    auto prepare = [&](uint64_t t, uint32_t slot, unsigned long long &toff) -> uint64_t {
+    // Tile counter -> local base index (tile bits and ownership bits clear): the counter's bits
+    // are spread over the positions hdr.fixed_mask leaves free.  The CTA's first tile is expanded
+    // run by run; every further one is a masked addition (carries ripple through the fixed
+    // positions because they are set to 1 for the addition).
+    auto expand = [&](uint64_t b) -> uint64_t {
+        for (uint32_t k = 0; k < hdr.n_runs; ++k) {
+            const uint32_t p = hdr.run_pos[k], len = hdr.run_len[k];
+            b = ((b >> p) << (p + len)) | (b & ((1ull << p) - 1ull));
+        }
+        return b;
+    };
+    const uint64_t fixed = hdr.fixed_mask;
+    const uint64_t step = expand(gridDim.x);
+    // Metadata of the first tile at or after (t, base), stepping by the grid, that some op of this
+    // pass can change: per-op flags (bit 7: controls outside the tile satisfied; bits 0-2:
+    // popcount of the diagonal target mask over the bits outside the tile, mod 8) and the tile's
+    // byte offset inside the shard.  Tiles no op touches (multi-controlled gates) are skipped
+    // without being read.  Passes whose ops do not look outside the tile skip all of this.
+    auto prepare = [&](uint64_t &t, uint64_t &base, uint32_t slot, unsigned long long &toff) {
         uint8_t *flags = s_flags_all + slot * flags_stride;
-        for (; t < hdr.n_tiles; t += gridDim.x) {
-            uint64_t base = t;               // tile counter -> local base index (tile bits clear)
-            for (uint32_t k = 0; k < hdr.n_runs; ++k) {
-                const uint32_t p = hdr.run_pos[k], len = hdr.run_len[k];
-                base = ((base >> p) << (p + len)) | (base & ((1ull << p) - 1ull));
-            }
-            base |= hdr.fx_val;
-            toff = base * 16ull;
-            base |= hdr.base_or;
+        for (; t < hdr.n_tiles; t += gridDim.x, base = ((base | fixed) + step) & ~fixed) {
+            const uint64_t lb = base | hdr.fx_val;
+            toff = lb * 16ull;
+            if (!need_flags) return;
+            const uint64_t gb = lb | hdr.base_or;
             int any = 0;
             for (uint32_t o = tid; o < n_ops; o += nthr) {
                 const MBase b = s_bases[o];
-                const uint32_t okb = ((~base & b.ctrl_base) == 0) ? 0x80u : 0u;
-                flags[o] = (uint8_t)(okb | ((uint32_t)__popcll(base & b.a_base) & 7u));
+                const uint32_t okb = ((~gb & b.ctrl_base) == 0) ? 0x80u : 0u;
+                flags[o] = (uint8_t)(okb | ((uint32_t)__popcll(gb & b.a_base) & 7u));
                 any |= (int)okb;
             }
-            if (__syncthreads_or(any)) return t;
+            if (__syncthreads_or(any)) return;
         }
-        return hdr.n_tiles;
     };
-    // 2^(T-L) chunks of 2^L contiguous amplitudes, 16-byte cp.async, swizzled; one commit group.
-    // Element j = tid + i * nthr: swz is GF(2)-linear and the thread count a power of two, so the
-    // shared-memory slot is swz(tid) ^ swz(i * nthr); with nthr a multiple of the chunk length the
-    // offset inside the chunk is the thread's own and the chunk index advances by nthr >> L.
-    const uint32_t my_slot = 16u * swz(tid);
+    // BULK: one cp.async.bulk per chunk, all completing on the mbarrier; the copies are issued by lane
+    // 0 of every warp (a warp's lanes would be serialised anyway: UBLKCP takes uniform operands), so
+    // no warp is held up longer than n_chunks / warps issues.
+    // !BULK: one 16-byte cp.async per amplitude; element j = tid + i * nthr, so with nthr a multiple
+    // of the chunk length every iteration advances the chunk by nthr >> L and keeps the offset.
     const bool regular = (nthr & lmask) == 0u && (tile_len % nthr) == 0u;
-    auto issue_load = [&](const unsigned long long toff, uint32_t bslot) {
-        const uint32_t tb_s = tiles_s + bslot * tile_bytes;
-        if (hdr.sysload) {
-            // peer tiles: system-scope loads (never served from a requester-side cache)
-            for (uint32_t j = tid; j < tile_len; j += nthr) {
-                const unsigned long long p = s_ptr0[j >> L] + toff + (unsigned long long)(j & lmask) * 16ull;
-                double a, b;
-                asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];\n" : "=d"(a), "=d"(b) : "l"(p) : "memory");
-                asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(tb_s + 16u * swz(j)), "d"(a), "d"(b) : "memory");
+    auto issue_load = [&](const unsigned long long toff) {
+        if (BULK) {
+            if ((tid & 31u) == 0u) {
+                if (tid == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the buffer was last touched by ld/st.shared
+                    mbar_expect_tx(mbar, 16u << T);
+                }
+                const uint32_t nw = nthr >> 5;
+                for (uint32_t c = tid >> 5; c < n_chunks; c += nw)
+                    bulk_g2s(tile_s + c * chunk_stride, s_ptr0[c] + toff, chunk_bytes, mbar);
             }
-            asm volatile("cp.async.commit_group;\n" ::: "memory");
-            return;
-        }
-        if (regular) {
+        } else if (regular) {
             const unsigned long long mine = toff + (unsigned long long)(tid & lmask) * 16ull;
-            const uint32_t cstep = (nthr >> L) * 8u;
-            uint32_t ch = ptr0_s + (tid >> L) * 8u;
-            for (uint32_t jb = 0; jb < tile_len; jb += nthr, ch += cstep) {
+            const uint32_t cstep = (nthr >> L) * 8u, dstep = (nthr >> L) * chunk_stride;
+            uint32_t ch = ptr0_s + (tid >> L) * 8u, d = tile_s + 16u * slot16(tid, L);
+#pragma unroll 4
+            for (uint32_t jb = 0; jb < tile_len; jb += nthr, ch += cstep, d += dstep) {
                 unsigned long long p;
                 asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(p) : "r"(ch) : "memory");
                 p += mine;
-                const uint32_t d = tb_s + (my_slot ^ (16u * swz(jb)));
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(p) : "memory");
             }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
         } else {
             for (uint32_t j = tid; j < tile_len; j += nthr) {
                 const unsigned long long p = s_ptr0[j >> L] + toff + (unsigned long long)(j & lmask) * 16ull;
-                const uint32_t d = tb_s + 16u * swz(j);
+                const uint32_t d = tile_s + 16u * slot16(j, L);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(p) : "memory");
             }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
         }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
 
-    uint32_t mslot = 0, bslot = 0;
+    // The CTA has ONE tile buffer, so the shared-memory load of tile i+1 cannot start before the last
+    // stage of tile i; to keep the HBM latency off that path the chunks of tile i+1 are prefetched
+    // into L2 a whole tile earlier (hdr.prefetch), and the late load finds them there.
+    auto prefetch_tile = [&](const unsigned long long toff) {
+        if ((tid & 31u) == 0u) {
+            const uint32_t nw = nthr >> 5;
+            for (uint32_t c = tid >> 5; c < n_chunks; c += nw) bulk_prefetch_l2(s_ptr0[c] + toff, chunk_bytes);
+        }
+    };
+
+    uint32_t mslot = 0, phase = 0;
     unsigned long long toff_cur = 0, toff_next = 0;
-    uint64_t t_cur = prepare(blockIdx.x, mslot, toff_cur);
-    if (t_cur < hdr.n_tiles) issue_load(toff_cur, bslot);
+    uint64_t t_cur = blockIdx.x, base_cur = expand(blockIdx.x);
+    prepare(t_cur, base_cur, mslot, toff_cur);
+    if (t_cur < hdr.n_tiles) issue_load(toff_cur);
     while (t_cur < hdr.n_tiles) {
         const uint32_t mnext = mslot + 1u == META_SLOTS ? 0u : mslot + 1u;
-        const uint64_t t_next = prepare(t_cur + gridDim.x, mnext, toff_next);
+        uint64_t t_next = t_cur + gridDim.x, base_next = ((base_cur | fixed) + step) & ~fixed;
+        prepare(t_next, base_next, mnext, toff_next);
         const bool has_next = t_next < hdr.n_tiles;
-        if (NB == 2 && has_next) {
-            issue_load(toff_next, bslot ^ 1u);
-            asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+        if (BULK) {
+            mbar_wait(mbar, phase);
+            phase ^= 1u;
+            if (need_flags) __syncthreads();           // this tile's flag bytes
         } else {
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            __syncthreads();
         }
-        __syncthreads();
-        const uint32_t tile_s = tiles_s + bslot * tile_bytes;
+        const uint8_t *flags = s_flags_all + mslot * flags_stride;
         const uint32_t flags_s = flags_all_s + mslot * flags_stride;
+        if (hdr.prefetch && has_next) prefetch_tile(toff_next);
 
         for (uint32_t s = 0; s < n_stages; ++s) {
             const bool last = s + 1 == n_stages;
@@ -832,30 +883,31 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
             amp v[NV];
             StageCtx x;
             if (active) {
-                x = stage_ctx(stages_s + 32u * s, jltab_s + 4u * (s * nthr + tid), ctab_s + 16u * s);
+                x = stage_ctx(s_stages + s, s_jltab + (s * nthr + tid), s_ctab + s);
                 if (last) x.goff = s_goff[tid];
                 stage_load(tile_s, x, v);
             }
-            if (last && NB == 1) {
+            if (last) {
                 __syncthreads();                       // every thread holds its amplitudes: the buffer is free
-                if (has_next) issue_load(toff_next, bslot);
-            } else if (!last && s_stages[s].sync_after_load) {
+                if (has_next) issue_load(toff_next);
+            } else if (s_stages[s].sync_after_load) {
                 // a lazy x makes threads store into each other's slots of the tile buffer: nobody
                 // may store before everybody has loaded
                 __syncthreads();
             }
             if (active) {
+                uint32_t inv = 0;
                 if (FULL) stage_ops_full(ops_s, flags_s, ob, oe, tid, mats, v);
-                else stage_ops_fast(ops_s, flags_s, ob, oe, tid, x, v);
-                if (!last) stage_store_smem(tile_s, x, v);
-                else if (hdr.touches_peer) stage_store_global(ptr0_s, L, toff_cur, x, v);
-                else stage_store_global_local(shard_base + toff_cur, gpos_s, x, v);
+                else stage_ops_fast(reinterpret_cast<const unsigned char *>(s_ops), flags, ob, oe, tid, L, x, inv, v);
+                if (!last) stage_store_smem(tile_s, x, inv, v);
+                else if (hdr.touches_peer) stage_store_global(ptr0_s, L, toff_cur, x, inv, v);
+                else stage_store_global_local(shard_base + toff_cur, s_gpos, x, inv, v);
             }
             if (!last) __syncthreads();
         }
         mslot = mnext;
-        if (NB == 2) bslot ^= 1u;
         t_cur = t_next;
+        base_cur = base_next;
         toff_cur = toff_next;
     }
     // Stores into a peer's HBM must be performed at SYSTEM scope before the barrier kernel that
@@ -866,60 +918,64 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
 
 constexpr size_t TILE_SMEM_MAX = 227u * 1024u;
 
-static size_t tile_smem_bytes(const TPassHdr &h, int nb, int threads = 256) {
-    return (size_t)nb * ((size_t)16 << h.T) + (size_t)(MOP_BYTES + sizeof(MBase)) * h.n_ops + (size_t)32 * h.n_stages +
-           ((size_t)8 << (h.T - h.L)) + 8 + (size_t)META_SLOTS * ((h.n_ops + 15u) & ~15u) +
-           (size_t)8 * threads + (size_t)16 * h.n_stages + (size_t)4 * threads * h.n_stages + 16;
+static size_t tile_smem_bytes(const TPassHdr &h, int threads) {
+    return ((size_t)16 << h.T) + ((size_t)16 << (h.T - h.L)) + 16 + (size_t)(MOP_BYTES + sizeof(MBase)) * h.n_ops +
+           (size_t)32 * h.n_stages + (((size_t)8 << (h.T - h.L)) + 8) + (size_t)8 * threads + (size_t)16 * h.n_stages +
+           (size_t)4 * threads * h.n_stages + 16 + (size_t)META_SLOTS * ((h.n_ops + 15u) & ~15u);
 }
 
 typedef void (*tile_kernel_t)(const Segs, const TPassHdr, const TStage *, const MOp *, const MBase *, const amp *);
 
-template <int THREADS, int MINB, int NB>
-static tile_kernel_t pick_kernel(bool full) {
-    return full ? k_tile_pass<THREADS, MINB, NB, true> : k_tile_pass<THREADS, MINB, NB, false>;
+template <int THREADS, int MINB>
+static tile_kernel_t pick_kernel(bool full, bool bulk) {
+    if (full) return bulk ? k_tile_pass<THREADS, MINB, true, true> : k_tile_pass<THREADS, MINB, true, false>;
+    return bulk ? k_tile_pass<THREADS, MINB, false, true> : k_tile_pass<THREADS, MINB, false, false>;
 }
 
+static tile_kernel_t select_kernel(int threads, int ctas, bool full, bool bulk) {
+    if (threads == 256) return pick_kernel<256, 2>(full, bulk);
+    if (ctas == 3) return pick_kernel<128, 3>(full, bulk);
+    if (ctas == 5) return pick_kernel<128, 5>(full, bulk);
+    return pick_kernel<128, 4>(full, bulk);
+}
+
+// cudaFuncSetAttribute is per device and costs a driver call per kernel: once per process and device.
 int tile_kernel_setup() {
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev]) return 0;
     bool ok = true;
-    for (int full = 0; full < 2; ++full) {
-        const tile_kernel_t ks[6] = {pick_kernel<128, 3, 2>(full), pick_kernel<128, 3, 1>(full),
-                                     pick_kernel<256, 2, 1>(full), pick_kernel<256, 1, 2>(full),
-                                     pick_kernel<128, 4, 1>(full), pick_kernel<128, 5, 1>(full)};
-        for (tile_kernel_t k : ks)
-            ok = ok && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)TILE_SMEM_MAX) == cudaSuccess;
-    }
+    for (int full = 0; full < 2; ++full)
+        for (int bulk = 0; bulk < 2; ++bulk)
+            for (int cfg = 0; cfg < 4; ++cfg) {
+                const tile_kernel_t k = select_kernel(cfg == 0 ? 256 : 128, cfg == 1 ? 3 : cfg == 2 ? 5 : 4, full, bulk);
+                ok = ok && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)TILE_SMEM_MAX) == cudaSuccess;
+            }
+    done[dev] = ok;
     return ok ? 0 : -1;
 }
 
-int g_tile_stagger = 0;      // experiment knob (option "tile_stagger"): start offset between the CTAs of an SM, cycles (no measurable effect)
-int g_tile_sysload = 0;    // debug/safety knob (option "tile_sysload"): system-scope loads for peer tiles
-int g_tile_nbuf = 0;     // tuning knob (option "tile_nbuf"): 0 = auto, 1 / 2 = force the buffer count
-
 int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, const TStage *d_stages,
-                     const MOp *d_ops, const MBase *d_bases, const amp *mat_table, int sm_count) {
+                     const MOp *d_ops, const MBase *d_bases, const amp *mat_table, int sm_count,
+                     const TileKnobs &knobs) {
     if (hdr.T < TILE_MIN_BITS || hdr.T > TILE_MAX_BITS || hdr.L > hdr.T || hdr.T - hdr.L > TILE_MAX_HIGH ||
         hdr.n_tiles == 0 || hdr.n_ops == 0 || hdr.n_ops > (uint32_t)TILE_MAX_OPS ||
         hdr.n_stages > (uint32_t)TILE_MAX_STAGES)
         return -1;
-    tile_kernel_t kern;
-    int threads, nb;
+    int threads;
     if (hdr.T >= 12) {
         threads = 256;
-        nb = g_tile_nbuf == 2 ? 2 : 1;
-        if (nb == 2 && tile_smem_bytes(hdr, 2) > TILE_SMEM_MAX) nb = 1;
-        kern = nb == 2 ? pick_kernel<256, 1, 2>(hdr.full != 0) : pick_kernel<256, 2, 1>(hdr.full != 0);
     } else {
         threads = 1 << (hdr.T - TILE_R);
         if (threads < 32) threads = 32;
         if (threads > 128) threads = 128;
-        nb = g_tile_nbuf == 2 ? 2 : 1;
-        if (nb == 2 && tile_smem_bytes(hdr, 2) > TILE_SMEM_MAX) nb = 1;
-        kern = nb == 2 ? pick_kernel<128, 3, 2>(hdr.full != 0)
-                       : g_tile_nbuf == 3 ? pick_kernel<128, 3, 1>(hdr.full != 0)
-                       : g_tile_nbuf == 5 ? pick_kernel<128, 5, 1>(hdr.full != 0) : pick_kernel<128, 4, 1>(hdr.full != 0);
     }
-    const size_t smem = tile_smem_bytes(hdr, nb, threads);
+    const tile_kernel_t kern = select_kernel(threads == 256 ? 256 : 128, knobs.ctas_per_sm, hdr.full != 0, knobs.bulk != 0);
+    const size_t smem = tile_smem_bytes(hdr, threads);
     if (smem > TILE_SMEM_MAX) return -1;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1)
@@ -927,9 +983,7 @@ int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, con
     uint64_t grid = (uint64_t)sm_count * per_sm;
     if (grid > hdr.n_tiles) grid = hdr.n_tiles;
     TPassHdr h2 = hdr;
-    h2.waves = (uint32_t)per_sm;
-    h2.stagger_cycles = grid > (uint64_t)sm_count ? (uint32_t)g_tile_stagger : 0u;
-    h2.sysload = (g_tile_sysload && hdr.touches_peer) ? 1u : 0u;
+    h2.prefetch = knobs.prefetch ? 1u : 0u;
     kern<<<(unsigned)grid, threads, smem, st>>>(segs, h2, d_stages, d_ops, d_bases, mat_table);
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }

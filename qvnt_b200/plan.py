@@ -22,6 +22,7 @@ class PlanOp:
     form: int
     ra: int
     rb: int
+    scale: float = 0.0      # h1: the butterfly factor (1/sqrt2; halves of a split h2: 1 and 0.5)
 
 
 @dataclass
@@ -37,6 +38,8 @@ class PlanMop:
     ctrl_base: int
     a_base: int
     src: int = -1
+    alt: List[float] = field(default_factory=list)
+    idx: int = 0
 
 
 @dataclass
@@ -103,9 +106,10 @@ def describe(q_num: int, circ, rank: int = 0, world: int = 1, peers: bool = Fals
                 code=int(kv["code"]), flags=int(kv["flags"]), okmask=int(kv["okmask"]), ctrl_thr=int(kv["ctrl_thr"]),
                 a_thr=int(kv["a_thr"]), a_reg=int(kv["a_reg"]),
                 c=[float.fromhex(kv[k]) for k in ("c0", "c1", "c2", "c3")],
-                ctrl_base=int(kv["ctrl_base"]), a_base=int(kv["a_base"]), src=last_src))
+                ctrl_base=int(kv["ctrl_base"]), a_base=int(kv["a_base"]), src=last_src,
+                alt=[float.fromhex(kv[k]) for k in ("a0", "a1", "a2", "a3")], idx=int(kv["idx"])))
         elif tok[0] == "op":
-            o = PlanOp(**{k: int(v) for k, v in kv.items()})
+            o = PlanOp(**{k: (float.fromhex(v) if k == "scale" else int(v)) for k, v in kv.items()})
             last_src = o.src
             if o.form == 6:          # header of a merged diagonal run: not an op of its own
                 continue

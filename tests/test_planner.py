@@ -43,6 +43,9 @@ def check_structure(passes, q_num, world=1, rank=0):
                 if o.form == 5:                                    # lazy x: a permutation between threads
                     assert o.kind == op.K_X and o.a & tile_mask == o.a
                     assert (o.a | o.ctrl) & sum(1 << g for g in regs) == 0
+                elif o.form == 7:                                  # lazy x on a register slot: slot marked inverted
+                    assert o.kind == op.K_X and 1 << regs[o.ra] == o.a
+                    assert o.ctrl & sum(1 << g for g in regs) == 0
                 elif o.form == 1:
                     assert 1 << regs[o.ra] == o.a
                 elif o.form in (2, 3):
@@ -67,7 +70,10 @@ def planned_sequence(passes, circ):
             assert s.ctrl == o.ctrl
             if s.kind == op.K_H2 and o.kind == op.K_H1:
                 assert o.a in (s.a_mask, s.b_mask)
-                s = single.h1(o.a)
+                # the half exactly as the planner scheduled it: a butterfly scaled by o.scale (1 and 0.5,
+                # not 1/sqrt2 twice), so replaying one half through the oracle and emulating the other agree
+                f = o.scale
+                s = SingleOp(op.K_U1, o.a, matrix=[complex(f), complex(f), complex(f), complex(-f)])   # (not unitary alone)
                 if o.ctrl:
                     s = s.c(o.ctrl)
             else:

@@ -34,8 +34,8 @@ def _emulate(oracle, n, circ, psi, world=1, **kw):
             assert not p.direct and not p.full and p.gpos == p0.gpos
             emu.run_tile_pass(psi, p)
         for st in p0.stages:
-            n_lazy += sum(1 for m in st.mops if m.code == emu.FC_LX)
-            n_runs += sum(1 for m in st.mops if m.code == emu.FC_DM)
+            n_lazy += sum(1 for m in st.mops if m.code in (emu.FC_LX, emu.FC_LI))
+            n_runs += sum(1 for m in st.mops if m.code in (emu.FC_DM, emu.FC_DM + emu.FC_MASKED))
     return psi, n_fast, n_lazy, n_runs
 
 

@@ -15,8 +15,8 @@ from __future__ import annotations
 
 import numpy as np
 
-FC_PR, FC_PX, FC_SW, FC_DU, FC_DS, FC_DG, FC_PA, FC_LX, FC_DM, FC_ALL = 0, 4, 8, 12, 13, 17, 18, 22, 23, 24
-MOP_SKIP0 = 0x02
+FC_PR, FC_PX, FC_DS, FC_DU, FC_DG, FC_LX, FC_LI, FC_DM, FC_MASKED, FC_SW = 0, 4, 8, 12, 13, 14, 15, 16, 17, 34
+MOP_SKIP0, MOP_COND, MOP_PARB, MOP_CONDB = 0x02, 0x04, 0x08, 0x10
 NV = 16
 U64 = (1 << 64) - 1
 
@@ -31,7 +31,10 @@ def _pc(x: int) -> int:
 
 def run_stage(tile: np.ndarray, st, T: int, gbase: int):
     """One stage on one tile (in place).  `gbase`: global index of the tile's first amplitude
-    (tile bits clear, rank bits included) -- what the kernel's prepare() derives the flags from."""
+    (tile bits clear, rank bits included) -- what the kernel's prepare() derives the flags from.
+
+    Registers are modelled the way the kernel holds them: regs[g, K] is PHYSICAL register K of
+    thread g; after lazy inversions (FC_LI) it holds the amplitude of slot pattern K ^ ib[g]."""
     G = 1 << (T - 4)
     grp = np.arange(G, dtype=np.int64)
     jl = np.zeros(G, dtype=np.int64)
@@ -45,94 +48,146 @@ def run_stage(tile: np.ndarray, st, T: int, gbase: int):
     regs = tile[jl[:, None] | kbits[None, :]].copy()          # G x 16
     vgrp = grp.copy()
     jl_cur = jl.copy()
+    ib = np.zeros(G, dtype=np.int64)                          # inverted slots per thread
     mops = st.mops
     i = 0
+
+    def cond(m):
+        # the kernel tests controls only for ops flagged MOP_COND / MOP_CONDB: the flags must be right
+        act = np.ones(G, dtype=bool)
+        if m.ctrl_thr or m.ctrl_base:
+            assert m.flags & MOP_COND, "op with thread / outer controls must carry MOP_COND"
+        if m.ctrl_base:
+            assert m.flags & MOP_CONDB
+        if m.flags & MOP_COND:
+            act &= (~vgrp & m.ctrl_thr) == 0
+            if m.flags & MOP_CONDB:
+                act &= (~gbase & m.ctrl_base & U64) == 0
+        return act
+
+    def dpar(m):
+        if m.a_base:
+            assert m.flags & MOP_PARB, "diagonal op with target bits outside the tile must carry MOP_PARB"
+        c = _popc(vgrp & m.a_thr)
+        if m.flags & MOP_PARB:
+            c = c + (_pc(gbase & m.a_base) & 7)
+        return c & 1
+
+    def okmask(m, masked):
+        if not masked:
+            assert m.okmask == 0xFFFF, "unmasked arms ignore okmask: only without slot controls"
+            return np.full((G, NV), True)
+        # register K holds slot pattern K ^ ib: its predicate is okmask bit K ^ ib (perm_ok)
+        Ks = np.arange(NV)[None, :] ^ ib[:, None]
+        return ((m.okmask >> Ks) & 1).astype(bool)
+
     while i < len(mops):
         m = mops[i]
         code = m.code
-        ok = m.okmask
-        if code >= FC_ALL:
-            code -= FC_ALL
-            assert m.okmask == 0xFFFF, "ALL arms ignore okmask: the planner must only use them without slot controls"
-            ok = 0xFFFF
-        okb = (~gbase & m.ctrl_base & U64) == 0
-        par_base = _pc(gbase & m.a_base) & 7
-        act = np.full(G, okb) & ((~vgrp & m.ctrl_thr) == 0)
-        c0, c1, c2, c3 = m.c
+        masked = False
+        if FC_MASKED <= code < FC_SW:
+            code -= FC_MASKED
+            masked = True
+        elif code >= FC_SW:
+            masked = True
+        act = cond(m)
         if code == FC_DM:
             cnt = m.a_reg
+            okm = okmask(m, masked)
             acc = np.ones(G, dtype=np.complex128)
             for k in range(1, cnt + 1):
                 e = mops[i + k]
-                assert e.code in (FC_DU, FC_ALL + FC_DU) and e.okmask == m.okmask and e.ctrl_thr == m.ctrl_thr \
+                assert e.code in (FC_DU, FC_MASKED + FC_DU) and e.okmask == m.okmask and e.ctrl_thr == m.ctrl_thr \
                     and e.ctrl_base == m.ctrl_base
-                par = (_popc(vgrp & e.a_thr) + (_pc(gbase & e.a_base) & 7)) & 1
+                par = dpar(e)
                 f = np.where(par == 1, complex(e.c[2], e.c[3]), complex(e.c[0], e.c[1]))
                 if e.flags & MOP_SKIP0:
                     f = np.where(par == 1, f, 1.0)
                 acc = acc * f
             for K in range(NV):
-                if ok >> K & 1:
-                    regs[act, K] *= acc[act]
+                sel = act & okm[:, K]
+                regs[sel, K] *= acc[sel]
             i += cnt + 1
             continue
         if code == FC_LX:
+            assert not masked and m.okmask == 0xFFFF
             vgrp[act] ^= m.a_thr
             jl_cur[act] ^= 1 << (m.a_reg & 0xFF)
             i += 1
             continue
-        par = (_popc(vgrp & m.a_thr) + par_base) & 1
-        if FC_PR <= code < FC_DU or FC_PA <= code < FC_LX:
-            s = code & 3 if code < FC_DU else (code - FC_PA)
+        if code == FC_LI:
+            assert not masked and m.okmask == 0xFFFF
+            ib[act] ^= 1 << (m.a_reg & 3)
+            i += 1
+            continue
+        okm = okmask(m, masked)
+        if code < FC_DS:                                       # pair forms on slot s
+            s = code & 3
             form = code - s
             bit = 1 << s
+            inv = (ib >> s) & 1
+            c0 = np.where(inv == 1, m.alt[0], m.c[0])
+            c1 = np.where(inv == 1, m.alt[1], m.c[1])
+            c2 = np.where(inv == 1, m.alt[2], m.c[2])
+            c3 = np.where(inv == 1, m.alt[3], m.c[3])
             for K in range(NV):
-                if K & bit or not (ok >> K & 1):
-                    continue
-                p0, p1 = regs[act, K].copy(), regs[act, K | bit].copy()
-                if form == FC_PR:
-                    n0, n1 = c0 * p0 + c1 * p1, c2 * p0 + c3 * p1
-                elif form == FC_PX:
-                    n0, n1 = c0 * p0 - 1j * c1 * p1, -1j * c2 * p0 + c3 * p1
-                elif form == FC_PA:
-                    n0, n1 = (p0 + p1) * c0, (p0 - p1) * c0
-                else:
-                    assert form == FC_SW
-                    n0, n1 = p1, p0
-                regs[act, K], regs[act, K | bit] = n0, n1
-        elif code == FC_DU:
-            f = np.where(par == 1, complex(c2, c3), complex(c0, c1))
-            sel = act.copy()
-            if m.flags & MOP_SKIP0:
-                sel &= par == 1
-            for K in range(NV):
-                if ok >> K & 1:
-                    regs[sel, K] *= f[sel]
-        elif FC_DS <= code < FC_DG:
-            bit = 1 << (code - FC_DS)
-            f0 = np.where(par == 1, complex(c2, c3), complex(c0, c1))      # roles swap with the outer parity
-            f1 = np.where(par == 1, complex(c0, c1), complex(c2, c3))
-            skip0 = bool(m.flags & MOP_SKIP0) & (par == 0)
-            for K in range(NV):
-                if not (ok >> K & 1):
-                    continue
                 if K & bit:
-                    regs[act, K] *= f1[act]
+                    continue
+                sel = act & okm[:, K]
+                assert np.array_equal(okm[:, K], okm[:, K | bit])
+                p0, p1 = regs[sel, K].copy(), regs[sel, K | bit].copy()
+                if form == FC_PR:
+                    n0, n1 = c0[sel] * p0 + c1[sel] * p1, c2[sel] * p0 + c3[sel] * p1
                 else:
-                    sel = act & ~skip0
+                    assert form == FC_PX
+                    n0, n1 = c0[sel] * p0 - 1j * c1[sel] * p1, -1j * c2[sel] * p0 + c3[sel] * p1
+                regs[sel, K], regs[sel, K | bit] = n0, n1
+        elif code >= FC_SW:
+            bit = 1 << (code - FC_SW)
+            for K in range(NV):
+                if K & bit:
+                    continue
+                sel = act & okm[:, K]
+                assert np.array_equal(okm[:, K], okm[:, K | bit])
+                p0, p1 = regs[sel, K].copy(), regs[sel, K | bit].copy()
+                regs[sel, K], regs[sel, K | bit] = p1, p0
+        elif code == FC_DU:
+            par = dpar(m)
+            f = np.where(par == 1, complex(m.c[2], m.c[3]), complex(m.c[0], m.c[1]))
+            sel0 = act.copy()
+            if m.flags & MOP_SKIP0:
+                sel0 &= par == 1
+            for K in range(NV):
+                sel = sel0 & okm[:, K]
+                regs[sel, K] *= f[sel]
+        elif FC_DS <= code < FC_DU:
+            s = code - FC_DS
+            bit = 1 << s
+            par = dpar(m)
+            blk = ((ib >> s) & 1) ^ par                         # 1: the alt block (roles exchanged)
+            f0 = np.where(blk == 1, complex(m.alt[0], m.alt[1]), complex(m.c[0], m.c[1]))
+            f1 = np.where(blk == 1, complex(m.alt[2], m.alt[3]), complex(m.c[2], m.c[3]))
+            skip0 = bool(m.flags & MOP_SKIP0)
+            for K in range(NV):
+                if K & bit:
+                    sel = act & okm[:, K] & ((not skip0) | (blk == 0))
+                    regs[sel, K] *= f1[sel]
+                else:
+                    sel = act & okm[:, K] & ((not skip0) | (blk == 1))
                     regs[sel, K] *= f0[sel]
         elif code == FC_DG:
             a_reg = m.a_reg & 0xF
+            par = (dpar(m) + _popc(ib & a_reg)) & 1
             for K in range(NV):
-                if not (ok >> K & 1):
-                    continue
+                sel = act & okm[:, K]
                 pk = (par + _pc(K & a_reg)) & 1
-                f = np.where(pk == 1, complex(c2, c3), complex(c0, c1))
-                regs[act, K] *= f[act]
+                f = np.where(pk == 1, complex(m.c[2], m.c[3]), complex(m.c[0], m.c[1]))
+                regs[sel, K] *= f[sel]
         else:
             raise AssertionError(f"unknown fast code {m.code}")
         i += 1
-    dst = jl_cur[:, None] | kbits[None, :]
+    kk = np.arange(NV)[None, :] ^ ib[:, None]                   # register K holds slot pattern K ^ ib
+    dst = jl_cur[:, None] | kbits[kk]
     assert np.unique(dst).size == dst.size, "a stage's stores must cover every tile slot exactly once"
     tile[dst] = regs
 

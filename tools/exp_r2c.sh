@@ -1,0 +1,18 @@
+#!/bin/bash
+mkdir -p gpurun_out
+out=gpurun_out/r02c_sweep.txt; : > $out
+run() { echo "== $*" >> $out; timeout 300 python bench.py --qubits 30 --steps 2 --warmup 1 --no-cpu --no-check "$@" 2>>gpurun_out/r02c_err.txt | python -c "
+import sys,json
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: continue
+    r=d['roofline']; print(f\"{d['value']:.0f} gates/s {d['ms_per_step']:.0f} ms/step {r['avg_launch_ms']:.3f} ms/pass frac {r['frac']:.3f} passes {r['passes_per_step']} e2e {d['e2e']['value']:.0f}\")
+" >> $out; }
+run --tma 1 --opt prefetch=1
+run --tma 1 --opt prefetch=0
+run --tma 0 --opt prefetch=1
+run --tma 0 --opt prefetch=0
+run --tma 0 --opt prefetch=1 --chunk-bits 3
+run --tma 0 --opt prefetch=1 --tile-bits 10 --chunk-bits 3
+run --tma 0 --opt prefetch=1 --tile-bits 12
+cat $out

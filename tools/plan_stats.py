@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Micro-op composition of a workload's schedule (host only, no GPU): passes, stages, and how many
 ops run as which arm of the fast stage interpreter -- the instruction-cost model behind
-DESIGN.md section 9 (pair / diagonal arms: 64 FP64 instr per thread; register-swap x: 96 moves;
-lazy x: 3 instr; merged diagonal run members: ~20 instr)."""
+DESIGN.md section 9 (pair / diagonal arms: 64 FP64 instr per thread + ~16 of fetch / dispatch; x with a control in a register
+slot: 48 moves; lazy x: a few integer instr; merged diagonal run members: ~14 instr)."""
 import argparse
 import collections
 import os
@@ -12,11 +12,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from qvnt_b200 import plan, workloads  # noqa: E402
 
-NAMES = {0: "pair_real", 4: "pair_cross", 8: "swap_x", 12: "diag_thread", 13: "diag_slot", 17: "diag_generic",
-         18: "pair_addsub(h)", 22: "lazy_x", 23: "diag_run_header"}
-COST = {"pair_real": 110, "pair_cross": 112, "pair_addsub(h)": 110, "diag_thread": 110, "diag_slot": 110,
-        "diag_generic": 150, "swap_x": 80,      # (96 moves + 46 where the control holds, ~20 elsewhere)
-        "lazy_x": 25, "diag_run_header": 110, "diag_run_member": 20}
+NAMES = {0: "pair_real", 4: "pair_cross", 8: "diag_slot", 12: "diag_thread", 13: "diag_generic", 14: "lazy_x_thread",
+         15: "lazy_x_slot", 16: "diag_run_header", 34: "swap_x(ctrl in slot)"}
+COST = {"pair_real": 80, "pair_cross": 80, "diag_thread": 78, "diag_slot": 80,
+        "diag_generic": 120, "swap_x(ctrl in slot)": 70,      # (48 moves where the control holds)
+        "lazy_x_thread": 16, "lazy_x_slot": 10, "diag_run_header": 80, "diag_run_member": 14}
 
 
 def main():
@@ -47,10 +47,10 @@ def main():
                     cnt["diag_run_member"] += 1
                     skip -= 1
                     continue
-                c = m.code - 24 if m.code >= 24 else m.code
+                c = m.code - 17 if 17 <= m.code < 34 else m.code
                 base = max(k for k in NAMES if k <= c)
                 cnt[NAMES[base]] += 1
-                if base == 23:
+                if base == 16:
                     skip = m.a_reg
     s = plan.summary(ps)
     print(f"{len(circ)} SingleOps -> {s['passes']} passes ({direct} direct, {full} full-interpreter, "

@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--qubits", type=int, default=36)
     ap.add_argument("--layers", type=int, default=4)
     ap.add_argument("--u", type=float, default=0.6180339887)
-    ap.add_argument("--opt", nargs="*", default=[], help="library options key=value (fuse, tile_bits, chunk_bits, tile_nbuf)")
+    ap.add_argument("--opt", nargs="*", default=[], help="library options key=value (fuse, tile_bits, chunk_bits, tile_ctas, tma)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

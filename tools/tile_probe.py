@@ -32,18 +32,17 @@ def main():
     ap.add_argument("--qubits", type=int, default=28)
     ap.add_argument("--tile-bits", type=int, default=12)
     ap.add_argument("--chunk-bits", type=int, default=7)
-    ap.add_argument("--nbuf", type=int, default=0)
+    ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--tma", type=int, default=1)
     ap.add_argument("--no-mem", action="store_true")
-    ap.add_argument("--stagger", type=int, default=-1)
     ap.add_argument("--only-rx", type=int, default=0, help="run only the rx probe with this k (for ncu)")
     ap.add_argument("--only-rot8", type=int, default=0, help="run only the rot8 probe with this k (for ncu)")
     args = ap.parse_args()
     n = args.qubits
     reg = QReg.new(n)
     hi = [n - 1, n - 2, n - 3, n - 4, n - 5, n - 6, n - 7, n - 8]
-    reg.set_option("tile_nbuf", args.nbuf)
-    if args.stagger >= 0:
-        reg.set_option("tile_stagger", args.stagger)
+    reg.set_option("tile_ctas", args.ctas)
+    reg.set_option("tma", args.tma)
     for tb in ((12, 11) if not args.no_mem else ()):
         for cb in (7, 4):
             if tb - cb > 8:
@@ -56,7 +55,7 @@ def main():
             print(f"mem   T={tb} L={cb} passes={passes} ms/pass={ms:.3f} GB/s={bpl / ms / 1e6:.0f}", flush=True)
     reg.set_option("tile_bits", args.tile_bits)
     reg.set_option("chunk_bits", args.chunk_bits)
-    print(f"--- T={args.tile_bits} L={args.chunk_bits} nbuf={args.nbuf} stagger={args.stagger}")
+    print(f"--- T={args.tile_bits} L={args.chunk_bits} ctas={args.ctas} tma={args.tma}")
     if args.only_rot8:
         circ = MultiOp()
         for i in range(args.only_rot8):
