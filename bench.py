@@ -458,7 +458,7 @@ def run_ours(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
         "engine": {"fuse": not args.no_fuse, "tile_bits": args.tile_bits or 11, "chunk_bits": args.chunk_bits or 4,
-                   "tile_loads": "cp.async.bulk + mbarrier" if args.tma != 0 else "cp.async 16 B"},
+                   "tile_loads": "cp.async.bulk + mbarrier" if args.tma == 1 else "cp.async 16 B, two tile buffers"},
         "equivalent_unfused_gbs": value * 32 * (1 << n) / 1e9,
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
         "parity_check": parity,

@@ -344,10 +344,18 @@ public:
     ~QReg() { if (h_) qvnt_reg_destroy(h_); }                      // Drop
 
     N num() const { return q_num_; }
-    // quant.rs:186-200: Option<Self>; parallelism is the GPU's, the count is accepted and ignored
+    // quant.rs:186-200 with GPUs for threads: the register continues on n GPUs (1, 2, 4 or 8 of this
+    // box, sharded by its top qubits, state kept); nullopt for 0 or more than the box has
     std::optional<QReg> num_threads(size_t n) && {
-        if (n == 0) return std::nullopt;
-        return std::move(*this);
+        int ndev = 0;
+        qvnt_device_count(&ndev);
+        if (n == 0 || (n & (n - 1)) || n > 8 || n > (size_t)ndev) return std::nullopt;
+        qvnt_reg_t *h = nullptr;
+        check(qvnt_reg_set_gpus(h_, (uint32_t)n, &h));
+        QReg out(std::move(*this));
+        qvnt_reg_destroy(out.h_);
+        out.h_ = h;
+        return out;
     }
     void apply(const MultiOp &op) {                                // quant.rs:376
         const auto v = op.lower();

@@ -107,6 +107,14 @@ int qvnt_reg_create(uint32_t q_num, uint64_t state, qvnt_reg_t **out);
  * exchanges the blobs (any transport), and attaches its peers. */
 int qvnt_reg_create_sharded(uint32_t q_num, uint64_t state, uint32_t rank, uint32_t world,
                             int device, qvnt_reg_t **out);
+/* The same sharding driven from ONE host process through ONE handle -- the drop-in for
+ * `QReg::num_threads(n)` (quant.rs:186-200, threads.rs:42-52): n_gpus in {1, 2, 4, 8} of this
+ * box, shard k on device k.  Every entry point of this header accepts the handle; one host thread
+ * enqueues every shard's work before it waits for any. */
+int qvnt_reg_create_multi(uint32_t q_num, uint64_t state, uint32_t n_gpus, qvnt_reg_t **out);
+/* `QReg::num_threads(n)` on an existing register: a NEW handle on n_gpus GPUs holding the same
+ * state (the caller destroys the old one, as `num_threads(self)` consumes it). */
+int qvnt_reg_set_gpus(qvnt_reg_t *reg, uint32_t n_gpus, qvnt_reg_t **out);
 #define QVNT_IPC_BLOB_BYTES 256
 int qvnt_reg_export_ipc(qvnt_reg_t *reg, void *blob /* QVNT_IPC_BLOB_BYTES */);
 int qvnt_reg_attach_peers(qvnt_reg_t *reg, const void *blobs /* world * QVNT_IPC_BLOB_BYTES */);
@@ -153,6 +161,17 @@ int qvnt_reg_read(qvnt_reg_t *reg, uint64_t off, uint64_t cnt, double *host_re_i
 int qvnt_reg_write(qvnt_reg_t *reg, uint64_t off, uint64_t cnt, const double *host_re_im);
 /* tensor_prod / Mul (quant.rs:330-371,625-636): out = a (low qubits) x b. */
 int qvnt_reg_tensor_prod(qvnt_reg_t *a, qvnt_reg_t *b, qvnt_reg_t **out);
+/* combine / combine_with_unitary / linear_composition (quant.rs:245-328; crate-private and untested
+ * in the reference): out = (a | b) as the lower / upper half of a register one qubit larger,
+ * optionally mixed by a 2x2 matrix (row-major, interleaved re,im); reg = reg * c0 + other * c1. */
+int qvnt_reg_combine(qvnt_reg_t *a, qvnt_reg_t *b, qvnt_reg_t **out);
+int qvnt_reg_combine_unitary(qvnt_reg_t *a, qvnt_reg_t *b, const double *matrix8, qvnt_reg_t **out);
+int qvnt_reg_linear_composition(qvnt_reg_t *reg, qvnt_reg_t *other, double c0_re, double c0_im, double c1_re,
+                                double c1_im);
+/* sample_all (quant.rs:513-594): histogram of `count` shots (Gaussian approximation, no collapse)
+ * for all 2^q_num indices into host_out; `seed` keys the device's counter-based normal generator
+ * (the reference draws from thread_rng: statistical parity). */
+int qvnt_reg_sample_all(qvnt_reg_t *reg, uint64_t count, uint64_t seed, uint64_t *host_out);
 int qvnt_reg_sync(qvnt_reg_t *reg);
 
 /* ---- tuning / instrumentation --------------------------------------------- */

@@ -166,3 +166,29 @@ class OracleReg:
 def weighted_index(weights: np.ndarray, u: float) -> int:
     w = np.ascontiguousarray(weights, dtype=np.float64)
     return int(lib().qo_weighted_index(w.ctypes.data, w.size, float(u)))
+
+
+# -- crate-private register helpers of the reference, restated in numpy (small, elementwise) -------
+def combine(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """quant.rs:245-271: the two state vectors as lower / upper half of a register one qubit larger."""
+    return np.concatenate([a, b])
+
+
+def combine_with_unitary(a: np.ndarray, b: np.ndarray, c) -> np.ndarray:
+    """quant.rs:274-307: out[idx] = c[0]*a + c[1]*b where the new top bit is clear, c[2]*a + c[3]*b where set."""
+    c = [complex(z) for z in c]
+    return np.concatenate([c[0] * a + c[1] * b, c[2] * a + c[3] * b])
+
+
+def linear_composition(self_psi: np.ndarray, psi: np.ndarray, c) -> np.ndarray:
+    """quant.rs:310-328: self[i] = self[i]*c.0 + psi[i]*c.1."""
+    return self_psi * complex(c[0]) + psi * complex(c[1])
+
+
+def sample_all_moments(p: np.ndarray, count: int):
+    """quant.rs:513-594: mean and standard deviation of every histogram bin before rounding:
+    counts_i = c p_i + sqrt(c) (n_i - p_i sum_j n_j), n_i = sqrt(p_i) g_i, g ~ N(0, 1) i.i.d."""
+    c = float(count)
+    mean = c * p
+    var = c * (p * (1 - p) ** 2 + p ** 2 * (1 - p))          # = c p (1 - p)
+    return mean, np.sqrt(var)

@@ -47,6 +47,12 @@ PROTOTYPES = {
     "qvnt_device_count": (c_int, [POINTER(c_int)]),
     "qvnt_reg_create": (c_int, [c_uint32, c_uint64, POINTER(_REG)]),
     "qvnt_reg_create_sharded": (c_int, [c_uint32, c_uint64, c_uint32, c_uint32, c_int, POINTER(_REG)]),
+    "qvnt_reg_create_multi": (c_int, [c_uint32, c_uint64, c_uint32, POINTER(_REG)]),
+    "qvnt_reg_set_gpus": (c_int, [_REG, c_uint32, POINTER(_REG)]),
+    "qvnt_reg_combine": (c_int, [_REG, _REG, POINTER(_REG)]),
+    "qvnt_reg_combine_unitary": (c_int, [_REG, _REG, c_void_p, POINTER(_REG)]),
+    "qvnt_reg_linear_composition": (c_int, [_REG, _REG, c_double, c_double, c_double, c_double]),
+    "qvnt_reg_sample_all": (c_int, [_REG, c_uint64, c_uint64, c_void_p]),
     "qvnt_reg_export_ipc": (c_int, [_REG, c_void_p]),
     "qvnt_reg_attach_peers": (c_int, [_REG, c_void_p]),
     "qvnt_reg_clone": (c_int, [_REG, POINTER(_REG)]),

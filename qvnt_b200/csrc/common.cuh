@@ -15,6 +15,7 @@ constexpr int MAX_WORLD = 8;
 // index i resolves to seg[i >> shift] + (i & lmask).  world == 1: shift = q_num.
 struct Segs {
     amp *seg[MAX_WORLD];
+    unsigned int *ack[MAX_WORLD];   // per-tile handshake words of every shard (remap passes, tile.cu)
     uint32_t shift;      // local index bits n_local
     uint32_t rank;       // this GPU's rank
     uint32_t world_bits; // log2(world)

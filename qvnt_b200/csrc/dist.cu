@@ -21,7 +21,9 @@ struct IpcBlob {
     int32_t pid;
     uint64_t raw_psi, raw_mail;      // same-process attach (tests drive all shards from threads)
     cudaIpcMemHandle_t h_psi, h_mail;
-    unsigned char pad[QVNT_IPC_BLOB_BYTES - 16 - 8 - 16 - 2 * sizeof(cudaIpcMemHandle_t)];
+    uint64_t raw_ack;
+    cudaIpcMemHandle_t h_ack;        // per-tile handshake words of remap passes
+    char bus_id[QVNT_IPC_BLOB_BYTES - 16 - 8 - 16 - 8 - 3 * sizeof(cudaIpcMemHandle_t)];   // PCI bus id of the device (16 bytes)
 };
 static_assert(sizeof(IpcBlob) == QVNT_IPC_BLOB_BYTES, "blob size");
 constexpr uint32_t BLOB_MAGIC = 0x51564E54u;
@@ -118,6 +120,10 @@ extern "C" {
 
 int qvnt_reg_export_ipc(qvnt_reg_t *r, void *blob) {
     if (!r || !blob) return QVNT_ERR_INVALID;
+    if (!r->shards.empty()) {
+        set_error("a multi-GPU handle of one process has its shards attached already");
+        return QVNT_ERR_INVALID;
+    }
     QV_CUDA(cudaSetDevice(r->device));
     IpcBlob b;
     memset(&b, 0, sizeof(b));
@@ -132,18 +138,33 @@ int qvnt_reg_export_ipc(qvnt_reg_t *r, void *blob) {
     QV_CUDA(cudaStreamSynchronize(r->stream));
     QV_CUDA(cudaIpcGetMemHandle(&b.h_psi, r->psi));
     QV_CUDA(cudaIpcGetMemHandle(&b.h_mail, r->mailbox));
+    cudaDeviceGetPCIBusId(b.bus_id, (int)sizeof(b.bus_id), r->device);
+    b.bus_id[sizeof(b.bus_id) - 1] = 0;
+    b.raw_ack = (uint64_t)(uintptr_t)r->ack;
+    if (r->ack) QV_CUDA(cudaIpcGetMemHandle(&b.h_ack, r->ack));
     memcpy(blob, &b, sizeof(b));
     return QVNT_OK;
 }
 
 int qvnt_reg_attach_peers(qvnt_reg_t *r, const void *blobs) {
     if (!r || !blobs) return QVNT_ERR_INVALID;
+    if (!r->shards.empty()) {
+        set_error("a multi-GPU handle of one process has its shards attached already");
+        return QVNT_ERR_INVALID;
+    }
     QV_CUDA(cudaSetDevice(r->device));
     if (r->world == 1) {
         r->peers_attached = true;
         return QVNT_OK;
     }
     const IpcBlob *bl = (const IpcBlob *)blobs;
+    // Remap passes hand-shake tile by tile with the peer's kernel of the same pass, so both kernels
+    // must be RUNNING at the same time: guaranteed with one GPU per shard, impossible when shards
+    // share a GPU (a test configuration).  Every rank sees every blob and decides alike.
+    r->remap_possible = true;
+    for (uint32_t a = 0; a < r->world; ++a)
+        for (uint32_t b2 = a + 1; b2 < r->world; ++b2)
+            if (!strncmp(bl[a].bus_id, bl[b2].bus_id, sizeof(bl[a].bus_id))) r->remap_possible = false;
     for (uint32_t k = 0; k < r->world; ++k) {
         const IpcBlob &b = bl[k];
         if (b.magic != BLOB_MAGIC || b.rank != k || b.world != r->world || b.n_local != r->n_local) {
@@ -165,6 +186,7 @@ int qvnt_reg_attach_peers(qvnt_reg_t *r, const void *blobs) {
                 cudaGetLastError();
             }
             r->segs.seg[k] = (amp *)(uintptr_t)b.raw_psi;
+            r->segs.ack[k] = (unsigned int *)(uintptr_t)b.raw_ack;
             r->mail[k] = (unsigned long long *)(uintptr_t)b.raw_mail;
         } else {
             void *p = nullptr, *m = nullptr;
@@ -180,9 +202,20 @@ int qvnt_reg_attach_peers(qvnt_reg_t *r, const void *blobs) {
                 cudaGetLastError();
                 return QVNT_ERR_COMM;
             }
+            void *a = nullptr;
+            if (b.raw_ack) {
+                e = cudaIpcOpenMemHandle(&a, b.h_ack, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) {
+                    set_error("cudaIpcOpenMemHandle(handshake words of rank %u) failed: %s", k, cudaGetErrorString(e));
+                    cudaGetLastError();
+                    return QVNT_ERR_COMM;
+                }
+            }
             r->peer_ptr[k] = p;
             r->peer_mail[k] = m;
+            r->peer_ack[k] = a;
             r->segs.seg[k] = (amp *)p;
+            r->segs.ack[k] = (unsigned int *)a;
             r->mail[k] = (unsigned long long *)m;
         }
     }

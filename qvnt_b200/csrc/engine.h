@@ -112,6 +112,10 @@ enum FCode : uint8_t {
                     // register slot (okmask != 0xFFFF): per-slot-pattern predicates
     FC_SW = 34,   // + slot (always masked)
     FC_TOTAL = 38
+    // The code byte of a fast MOp also carries the op's CONTROL CLASS: code = arm + FC_TOTAL * cls,
+    // cls 0: unconditional, 1: controls on thread bits, 2: ... and outside the tile (MOP_COND /
+    // MOP_CONDB say the same).  The PTX op loop jumps on the whole byte (classes 1 / 2 land in a stub
+    // that tests the controls first), so unconditional ops never pay for the test.
 };
 constexpr uint8_t MOP_SKIP0 = 0x02;   // flags bit 1 (diagonal forms): f0 == 1, even parity untouched
 constexpr uint8_t MOP_COND = 0x04;    // flags bit 2: the op has controls on thread bits or outside the tile
@@ -119,6 +123,7 @@ constexpr uint8_t MOP_COND = 0x04;    // flags bit 2: the op has controls on thr
 constexpr uint8_t MOP_PARB = 0x08;    // flags bit 3 (diagonal forms): target bits outside the tile (a_base != 0):
                                       //   the per-tile flag byte carries their parity
 constexpr uint8_t MOP_CONDB = 0x10;   // flags bit 4: ... and some of them outside the tile (ctrl_base != 0): read the flag byte
+constexpr uint8_t MOP_ATHR = 0x20;    // flags bit 5 (diagonal forms): target bits on thread bits (a_thr != 0)
 constexpr uint32_t MOP_ALT_BYTES = 32; // byte distance from the coefficient block to the `alt` block
 
 struct __align__(16) MOp {   // 80 bytes, staged in shared memory
@@ -165,6 +170,14 @@ struct TPassHdr {
     uint64_t n_tiles;            // tiles this rank processes
     uint64_t base_or;            // this rank's bits for the global qubits that are NOT tile bits
     uint32_t touches_peer;       // some tile bit is a rank bit
+    // Remap pass: one tile bit is the rank bit remap_g and the pinned local bit is remap_b; the pass
+    // stores BOTH values of g into this rank's shard, at bit position b -- afterwards index bits g
+    // and b have traded places (the planner's logical -> physical qubit map records it).  Loads
+    // read the peer half through NVLink as in any peer pass; stores are all local, into places the
+    // PEER's CTA of the same tile reads, hence the per-tile handshake (tile.cu).
+    uint8_t remap, remap_g, remap_b, _pad3;
+    uint32_t epoch;              // remap handshake value of this pass (filled at launch)
+    uint8_t gpos_store[16];      // tile-local bit -> bit position the last stage stores it to (== gpos unless remap)
     uint32_t full;               // some op needs the full interpreter (u1/u2, two-bit pair ops, multi-bit masks)
     uint32_t need_flags;         // some op of the pass depends on index bits outside the tile (per-tile flag bytes)
     uint32_t prefetch;           // filled by launch_tile_pass (TileKnobs): L2 prefetch of the next tile's chunks
@@ -175,9 +188,12 @@ struct TPassHdr {
 
 // Per-handle tuning knobs of the tile pass (qvnt_reg_set_option): no process-global state.
 struct TileKnobs {
-    int ctas_per_sm = 0;   // 0 = auto (4 for 2^11 tiles, 2 for 2^12); 3 / 5: forced
-    int bulk = 1;          // 1: tile loads by cp.async.bulk (TMA) + mbarrier; 0: 16-byte cp.async
-    int prefetch = 1;      // 1: cp.async.bulk.prefetch.L2 of tile i+1 while tile i computes
+    int ctas_per_sm = 0;   // 0 = auto (3 x 128 threads at 168 registers for 2^11 tiles: no spills; 2 x 256 for 2^12); 4: forced
+    int bulk = 0;          // 1: tile loads by cp.async.bulk (TMA) + mbarrier; 0: 16-byte cp.async (measured faster
+                           //    at 256-byte chunks: a bulk copy costs its issuing lane ~17 instructions)
+    int prefetch = 0;      // 1: cp.async.bulk.prefetch.L2 of tile i+1 while tile i computes (measured: no gain, off)
+    int double_buffer = 0; // 1: two tile buffers per CTA where three CTAs per SM still fit (2^11 tiles, cp.async loads)
+    int ptx_ops = 1;       // 1: the fast interpreter's op loop as one inline-PTX block (fastops_ptx.inc); 0: C++ loop
 };
 int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, const TStage *d_stages,
                      const MOp *d_ops, const MBase *d_bases, const amp *mat_table, int sm_count,
@@ -200,6 +216,13 @@ int launch_scale(cudaStream_t st, amp *psi, uint64_t len, double f);
 int launch_set_basis(cudaStream_t st, amp *psi, uint64_t len, uint64_t one_at /* >= len: none */);
 int launch_tensor_prod(cudaStream_t st, const amp *a, uint32_t qa, const amp *b, uint32_t qb, amp *out,
                        uint64_t out_off, uint64_t out_len);
+int launch_combine_unitary(cudaStream_t st, const amp *a, const amp *b, uint32_t q, const double *m8, amp *out);
+int launch_linear_composition(cudaStream_t st, amp *self, const amp *other, uint64_t len, amp c0, amp c1);
+// sample_all: sum over i of sqrt(p_i) g_i -> *d_out; then the counts of [off, off + cnt) and their sum
+int launch_sample_noise_sum(cudaStream_t st, const amp *psi, uint64_t len, uint64_t idx_or, double inv, uint64_t seed,
+                            double *d_partials, double *d_out, int sm_count);
+int launch_sample_counts(cudaStream_t st, const amp *psi, uint64_t off, uint64_t cnt, uint64_t idx_or, double inv,
+                         uint64_t seed, double c, double n_sum, unsigned long long *d_out, unsigned long long *d_total);
 // measurement sampling, blocked-sequential cumulative order (see measure.cu)
 constexpr uint64_t SAMPLE_BLOCK = 1ull << 12;
 int launch_block_weights(cudaStream_t st, const amp *psi, uint64_t len, double inv, double *d_l1,

@@ -190,6 +190,112 @@ int launch_tensor_prod(cudaStream_t st, const amp *a, uint32_t qa, const amp *b,
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 
+// ---- combine / linear_composition (quant.rs:245-328, crate-private in the reference) ------------
+// out[idx] = top bit of idx clear ? c00*q0 + c01*q1 : c10*q0 + c11*q1, q = (a[idx & mask], b[idx & mask])
+__global__ void __launch_bounds__(256)
+k_combine_unitary(const amp *__restrict__ a, const amp *__restrict__ b, uint32_t q, amp c00, amp c01, amp c10,
+                  amp c11, amp *__restrict__ out) {
+    const uint64_t len = 2ull << q, mask = (1ull << q) - 1ull;
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < len; i += stride) {
+        const amp x = a[i & mask], y = b[i & mask];
+        const amp m0 = (i >> q) ? c10 : c00, m1 = (i >> q) ? c11 : c01;
+        const double r0 = m0.x * x.x - m0.y * x.y, i0 = m0.x * x.y + m0.y * x.x;       // num_complex Mul
+        const double r1 = m1.x * y.x - m1.y * y.y, i1 = m1.x * y.y + m1.y * y.x;
+        out[i] = make_double2(r0 + r1, i0 + i1);
+    }
+}
+int launch_combine_unitary(cudaStream_t st, const amp *a, const amp *b, uint32_t q, const double *m, amp *out) {
+    k_combine_unitary<<<stream_grid(2ull << q), 256, 0, st>>>(a, b, q, make_double2(m[0], m[1]), make_double2(m[2], m[3]),
+                                                             make_double2(m[4], m[5]), make_double2(m[6], m[7]), out);
+    return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
+}
+// self[i] = self[i] * c0 + other[i] * c1
+__global__ void __launch_bounds__(256)
+k_linear_composition(amp *__restrict__ self, const amp *__restrict__ other, uint64_t len, amp c0, amp c1) {
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < len; i += stride) {
+        const amp x = self[i], y = other[i];
+        const double r0 = x.x * c0.x - x.y * c0.y, i0 = x.x * c0.y + x.y * c0.x;
+        const double r1 = y.x * c1.x - y.y * c1.y, i1 = y.x * c1.y + y.y * c1.x;
+        self[i] = make_double2(r0 + r1, i0 + i1);
+    }
+}
+int launch_linear_composition(cudaStream_t st, amp *self, const amp *other, uint64_t len, amp c0, amp c1) {
+    k_linear_composition<<<stream_grid(len), 256, 0, st>>>(self, other, len, c0, c1);
+    return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
+}
+
+// ---- sample_all (quant.rs:513-594) ------------------------------------------------------------------
+// n_i = sqrt(p_i) * g_i with g_i ~ N(0, 1); counts_i = max(round(c p_i + sqrt(c) (n_i - p_i sum n)), 0).
+// g_i comes from a counter-based generator keyed by (seed, global index): the second pass recomputes
+// it instead of storing 8 bytes per amplitude.  (Statistical, not bit, parity: the reference draws
+// from thread_rng.)
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double gauss_at(uint64_t seed, uint64_t i) {
+    const uint64_t a = mix64(seed + 0x9E3779B97F4A7C15ull * (2 * i + 1)), b = mix64(seed + 0x9E3779B97F4A7C15ull * (2 * i + 2));
+    const double u1 = ((double)(a >> 11) + 1.0) * (1.0 / 9007199254740992.0);      // (0, 1]
+    const double u2 = (double)(b >> 11) * (1.0 / 9007199254740992.0);              // [0, 1)
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+__global__ void __launch_bounds__(256)
+k_sample_noise_sum(const amp *__restrict__ psi, uint64_t len, uint64_t idx_or, double inv, uint64_t seed,
+                   double *__restrict__ partials) {
+    double s = 0.0;
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < len; i += stride) {
+        const amp a = psi[i];
+        s += sqrt((a.x * a.x + a.y * a.y) * inv) * gauss_at(seed, idx_or | i);
+    }
+    const double r = block_sum_256(s);
+    if (threadIdx.x == 0) partials[blockIdx.x] = r;
+}
+__global__ void __launch_bounds__(256)
+k_sample_counts(const amp *__restrict__ psi, uint64_t off, uint64_t cnt, uint64_t idx_or, double inv, uint64_t seed,
+                double c, double c_sqrt, double n_sum, unsigned long long *__restrict__ out,
+                unsigned long long *__restrict__ total) {
+    unsigned long long t = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * 256;
+    for (uint64_t k = (uint64_t)blockIdx.x * 256 + threadIdx.x; k < cnt; k += stride) {
+        const uint64_t i = off + k;
+        const amp a = psi[i];
+        const double p = (a.x * a.x + a.y * a.y) * inv;
+        const double n = sqrt(p) * gauss_at(seed, idx_or | i);
+        const double v = round(c * p + c_sqrt * (n - n_sum * p));       // f64::round: half away from zero
+        const unsigned long long m = v > 0.0 ? (unsigned long long)v : 0ull;
+        out[k] = m;
+        t += m;
+    }
+    __shared__ unsigned long long sh[8];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0;
+        for (int w = 0; w < 8; ++w) s += sh[w];
+        atomicAdd(total, s);
+    }
+}
+int launch_sample_noise_sum(cudaStream_t st, const amp *psi, uint64_t len, uint64_t idx_or, double inv, uint64_t seed,
+                            double *d_partials, double *d_out, int sm_count) {
+    int g = sm_count * 8;
+    if (g > REDUCE_BLOCKS_MAX) g = REDUCE_BLOCKS_MAX;
+    if ((uint64_t)g * 256 > len) g = (int)((len + 255) / 256);
+    if (g < 1) g = 1;
+    k_sample_noise_sum<<<g, 256, 0, st>>>(psi, len, idx_or, inv, seed, d_partials);
+    k_sum_partials<<<1, 256, 0, st>>>(d_partials, g, d_out);
+    return cudaPeekAtLastError() == cudaSuccess ? 2 : -1;
+}
+int launch_sample_counts(cudaStream_t st, const amp *psi, uint64_t off, uint64_t cnt, uint64_t idx_or, double inv,
+                         uint64_t seed, double c, double n_sum, unsigned long long *d_out, unsigned long long *d_total) {
+    k_sample_counts<<<stream_grid(cnt), 256, 0, st>>>(psi, off, cnt, idx_or, inv, seed, c, sqrt(c), n_sum, d_out, d_total);
+    return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
+}
+
 // ---- sampling -------------------------------------------------------------
 // Level 1: one 256-thread CTA per SAMPLE_BLOCK (4096) amplitudes: thread t sums
 // its 16 weights w = |a|^2 * inv (strided by 256, fixed order), then the shuffle
@@ -261,38 +367,77 @@ __global__ void k_total(const double *__restrict__ l2, uint64_t n2, double *__re
     if (threadIdx.x == 0) *out = cum;
 }
 
+// Last index k < count with load(k) > 0, or `count` if there is none (lane-parallel, rare path).
+template <typename F>
+__device__ __forceinline__ uint64_t warp_last_positive(F load, uint64_t count) {
+    const unsigned lane = threadIdx.x & 31;
+    for (uint64_t top = count; top > 0;) {
+        const uint64_t base = top >= 32 ? top - 32 : 0;
+        const bool pos = base + lane < top && load(base + lane) > 0.0;
+        const unsigned m = __ballot_sync(0xffffffffu, pos);
+        if (m) return base + (31 - __clz(m));
+        top = base;
+    }
+    return count;
+}
+
 // result[0] = local index, result[1] = 1 if found in this shard, result[2] = bits of the
-// running sum reached (== prefix + shard total when not found).
+// running sum reached (== prefix + shard total when not found), result[3] = when not found: the
+// last local index with a non-zero weight (~0 if the shard is all zero).
+// rand 0.8.5 WeightedIndex never returns a zero-weight index; where rounding lets the sequential
+// walk run off the end of a block the blocked sums said holds the crossing, the answer is the last
+// index of that block with a non-zero weight, never a zero-probability one.
 __global__ void k_locate(const amp *__restrict__ psi, uint64_t len, double inv,
                          const double *__restrict__ l1, uint64_t n1, const double *__restrict__ l2,
                          uint64_t n2, double prefix, double x, uint64_t *__restrict__ result) {
     double cum = prefix;
+    auto w0 = [&](uint64_t i) {
+        const amp a = psi[i];
+        return (a.x * a.x + a.y * a.y) * inv;
+    };
     const uint64_t b2 = warp_seq_find([&](uint64_t i) { return l2[i]; }, n2, cum, x);
     if (b2 == n2) {
+        // not in this shard: report where its probability mass ends (the caller's fallback)
+        uint64_t last = ~0ull;
+        const uint64_t e2 = warp_last_positive([&](uint64_t i) { return l2[i]; }, n2);
+        if (e2 != n2) {
+            const uint64_t o1 = e2 * SAMPLE_BLOCK;
+            const uint64_t c1 = (n1 - o1) < SAMPLE_BLOCK ? (n1 - o1) : SAMPLE_BLOCK;
+            const uint64_t e1 = warp_last_positive([&](uint64_t i) { return l1[o1 + i]; }, c1);
+            if (e1 != c1) {
+                const uint64_t o0 = (o1 + e1) * SAMPLE_BLOCK;
+                const uint64_t c0 = (len - o0) < SAMPLE_BLOCK ? (len - o0) : SAMPLE_BLOCK;
+                const uint64_t e0 = warp_last_positive([&](uint64_t i) { return w0(o0 + i); }, c0);
+                if (e0 != c0) last = o0 + e0;
+            }
+        }
         if (threadIdx.x == 0) {
-            result[0] = len - 1;
+            result[0] = last != ~0ull ? last : len - 1;
             result[1] = 0;
             result[2] = (uint64_t)__double_as_longlong(cum);
+            result[3] = last;
         }
         return;
     }
     const uint64_t o1 = b2 * SAMPLE_BLOCK;
     const uint64_t c1 = (n1 - o1) < SAMPLE_BLOCK ? (n1 - o1) : SAMPLE_BLOCK;
     uint64_t b1 = warp_seq_find([&](uint64_t i) { return l1[o1 + i]; }, c1, cum, x);
-    if (b1 == c1) b1 = c1 - 1;  // rounding guard: tree sum said "inside", sequential walk disagrees
+    if (b1 == c1) {  // rounding guard: tree sum said "inside", sequential walk disagrees
+        b1 = warp_last_positive([&](uint64_t i) { return l1[o1 + i]; }, c1);
+        if (b1 == c1) b1 = c1 - 1;
+    }
     const uint64_t o0 = (o1 + b1) * SAMPLE_BLOCK;
     const uint64_t c0 = (len - o0) < SAMPLE_BLOCK ? (len - o0) : SAMPLE_BLOCK;
-    uint64_t b0 = warp_seq_find(
-        [&](uint64_t i) {
-            const amp a = psi[o0 + i];
-            return (a.x * a.x + a.y * a.y) * inv;
-        },
-        c0, cum, x);
-    if (b0 == c0) b0 = c0 - 1;
+    uint64_t b0 = warp_seq_find([&](uint64_t i) { return w0(o0 + i); }, c0, cum, x);
+    if (b0 == c0) {
+        b0 = warp_last_positive([&](uint64_t i) { return w0(o0 + i); }, c0);
+        if (b0 == c0) b0 = c0 - 1;
+    }
     if (threadIdx.x == 0) {
         result[0] = o0 + b0;
         result[1] = 1;
         result[2] = (uint64_t)__double_as_longlong(cum);
+        result[3] = o0 + b0;
     }
 }
 int launch_total(cudaStream_t st, const double *d_l2, uint64_t n2, double *d_out) {

@@ -28,7 +28,8 @@ static inline int pc64(uint64_t v) { return __builtin_popcountll(v); }
 static inline int ctz64(uint64_t v) { return __builtin_ctzll(v); }
 
 struct POp {
-    DevOp d;        // masks in GLOBAL numbering
+    DevOp d;        // masks in PHYSICAL index-bit numbering (== qubit numbering until a remap pass moves a qubit)
+    uint64_t la, lb, lctrl;   // the same masks in LOGICAL (qubit) numbering, as the caller gave them
     int cls;
     uint64_t mix;   // bits that must lie inside a tile / in registers
     uint64_t dg;    // bits the op is diagonal in (controls, diagonal targets)
@@ -38,7 +39,11 @@ struct POp {
 struct PlanCfg {
     uint32_t q_num, n_local, rank, world;
     bool peers, fuse;
+    bool remap = true;       // global-qubit passes leave the qubit local (logical -> physical map), see build_plan
     int tile_bits, chunk_bits;
+    uint8_t perm[64];        // logical qubit -> physical index bit at the start of the op list
+    uint64_t ack_cap = ~0ull; // tiles the per-tile handshake array of a remap pass can hold
+    int force_pinned = -1;    // restore_layout: the local bit a remap pass must trade the global bit with
     uint64_t q_mask() const { return q_num >= 64 ? ~0ull : ((1ull << q_num) - 1ull); }
 };
 
@@ -77,7 +82,6 @@ static int validate(const PlanCfg &r_, const qvnt_op_t &o, size_t k) {
 // ---- lowering: qvnt_op_t -> POp ------------------------------------------------------------
 static int lower_ops(const PlanCfg &r, const qvnt_op_t *ops, size_t n_ops, std::vector<POp> &pl,
                      std::vector<amp> &mats) {
-    const uint64_t gmask = r.q_mask() & ~((1ull << r.n_local) - 1ull);
     const bool tile_possible = r.n_local >= (uint32_t)TILE_MIN_BITS;
     // a lone SingleOp keeps the reference's exact arithmetic (one direct sweep); op LISTS are
     // refactored for the fused pass (exact factorisations, FMA arithmetic: parity bar 1e-10)
@@ -107,7 +111,7 @@ static int lower_ops(const PlanCfg &r, const qvnt_op_t *ops, size_t n_ops, std::
             p.d.mat = (uint32_t)mats.size();
             for (int i = 0; i < cnt; ++i) mats.push_back(make_double2(o.matrix[2 * i], o.matrix[2 * i + 1]));
         }
-        const bool split_masks = (r.fuse && tile_possible) || (o.a_mask & gmask);
+        const bool split_masks = (r.fuse && tile_possible) || r.world > 1;
         if (split_masks && (o.kind == QVNT_X || o.kind == QVNT_Y) && pc64(o.a_mask) > 1) {
             // x(m) = prod_b x(b), y(m) = prod_b y(b): permutations and i-power sign flips only,
             // so the factorisation is exact (y: i^(2*ones-k), atomic/y.rs:10-23).
@@ -158,7 +162,28 @@ static int lower_ops(const PlanCfg &r, const qvnt_op_t *ops, size_t n_ops, std::
         p.dg = p.d.ctrl | (p.cls == CLS_DIAG ? p.d.a : 0);
         pl.push_back(p);
     }
+    // logical (qubit) masks -> physical index bits under the register's current qubit map
+    auto xl = [&](uint64_t m) {
+        uint64_t o = 0;
+        for (; m; m &= m - 1) o |= 1ull << r.perm[ctz64(m)];
+        return o;
+    };
+    for (POp &p : pl) {
+        p.la = p.d.a;
+        p.lb = p.d.b;
+        p.lctrl = p.d.ctrl;
+        p.d.a = xl(p.d.a);
+        p.d.b = xl(p.d.b);
+        p.d.ctrl = xl(p.d.ctrl);
+        p.mix = xl(p.mix);
+        p.dg = xl(p.dg);
+    }
     return QVNT_OK;
+}
+
+static inline uint64_t swap_bits(uint64_t m, int i, int j) {
+    const uint64_t d = ((m >> i) ^ (m >> j)) & 1ull;
+    return m ^ ((d << i) | (d << j));
 }
 
 // ---- one direct sweep -----------------------------------------------------------------------
@@ -230,6 +255,7 @@ static void greedy_select(const std::vector<POp> &pl, const std::vector<int> &ca
 // Kinds the fast stage interpreter carries (tile.cu, FCode)
 static bool fast_kind(const POp &p) {
     switch (p.d.kind) {
+    case QVNT_ID: return true;      // placeholder of an empty remap pass (restore_layout): occupies a slot, emits nothing
     case QVNT_X: case QVNT_Y: case QVNT_RX: case QVNT_RY: case QVNT_H1:
     case QVNT_Z: case QVNT_S: case QVNT_T: case QVNT_RZ:
         return pc64(p.d.a) == 1;
@@ -243,6 +269,7 @@ static bool fast_kind(const POp &p) {
 struct MInfo { int src; int form, ra, rb; };   // host-side description of every MOp (describe / tests)
 
 struct Plan {
+    uint8_t perm[64];          // logical qubit -> physical index bit after the last pass
     std::vector<PassPlan> passes;
     std::vector<TStage> stages;
     std::vector<MOp> mops;
@@ -371,7 +398,7 @@ static void stage_select(const std::vector<POp> &pl, const std::vector<int> &can
 }
 
 // Pure host function (no CUDA): op list -> passes -> stages.
-static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) {
+static int build_plan(const PlanCfg &c, std::vector<POp> &pl, Plan &plan) {
     const uint32_t n_local = c.n_local;
     const uint64_t lmask = (1ull << n_local) - 1ull;
     const uint64_t qmask = c.q_mask();
@@ -388,10 +415,13 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
     if (L > T) L = T;
     if (T - L > (uint32_t)TILE_MAX_HIGH) L = T - TILE_MAX_HIGH;
     if (L + 2 > T) L = T >= 2 ? T - 2 : 0;      // keep room for the two gathered bits a two-qubit op may need
+    if (c.force_pinned >= 0 && (uint32_t)c.force_pinned < L) L = (uint32_t)c.force_pinned;   // the pinned bit is no tile bit
+    if (T - L > (uint32_t)TILE_MAX_HIGH) T = L + TILE_MAX_HIGH;
     const bool tile_ok = T >= (uint32_t)TILE_MIN_BITS && n_local >= (uint32_t)TILE_MIN_BITS;
     const uint64_t low = (1ull << L) - 1ull;
     const uint64_t rank_bits = (uint64_t)c.rank << n_local;
 
+    memcpy(plan.perm, c.perm, sizeof(plan.perm));
     std::vector<PassPlan> &passes = plan.passes;
     std::vector<int> cand(pl.size()), sel, rest;
     for (size_t i = 0; i < pl.size(); ++i) cand[i] = (int)i;
@@ -445,7 +475,8 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
             continue;
         }
         // fill the tile up to T bits with the lowest unused local bits (keeps it contiguous)
-        for (uint32_t b = L; pc64(set) < (int)T && b < n_local; ++b) set |= 1ull << b;
+        for (uint32_t b = L; pc64(set) < (int)T && b < n_local; ++b)
+            if ((int)b != c.force_pinned) set |= 1ull << b;
         // tile-local numbering: ascending global position
         TPassHdr &h = pp.hdr;
         h.T = (uint32_t)pc64(set);
@@ -455,9 +486,42 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
         const uint64_t tile_g = set & gmask;
         const int kg = pc64(tile_g);
         h.touches_peer = kg ? 1u : 0u;
-        // ownership: the kg highest local non-tile bits are pinned to this rank's tile-global bits
+        // ownership: kg local non-tile bits are pinned to this rank's tile-global bits.
+        // Remap pass (kg == 1, option "remap"): the pass does not write the peer half back -- every
+        // rank keeps BOTH values of the global bit g for its value of the pinned local bit b, i.e.
+        // index bits g and b trade places and the qubit that was global is local from here on
+        // (tile.cu: stores go to the local address with bit b := value of g).  The pinned bit is then
+        // chosen as the local bit whose qubit is needed latest (as a mix bit) by the remaining ops.
         uint64_t own_mask = 0, own_val = 0;
-        {
+        const bool remap = c.remap && kg == 1 && peers &&
+                           (1ull << (n_local - (uint32_t)pc64(set & lmask) - 1u)) <= c.ack_cap;
+        if (remap) {
+            const int gb = ctz64(tile_g);
+            int best = c.force_pinned;
+            size_t best_d = 0;
+            for (int b = (int)n_local - 1; b >= 0 && c.force_pinned < 0; --b) {
+                if ((set >> b) & 1) continue;
+                size_t d = rest.size() + 1;                  // never needed again
+                for (size_t k = 0; k < rest.size(); ++k)
+                    if ((pl[rest[k]].mix >> b) & 1) {
+                        d = k;
+                        break;
+                    }
+                if (best < 0 || d > best_d) {
+                    best = b;
+                    best_d = d;
+                }
+            }
+            if (best < 0) {
+                set_error("shard too small for a tile with a global bit");
+                return QVNT_ERR_UNSUPPORTED;
+            }
+            own_mask = 1ull << best;
+            if ((rank_bits >> gb) & 1ull) own_val = own_mask;
+            h.remap = 1;
+            h.remap_g = (uint8_t)gb;
+            h.remap_b = (uint8_t)best;
+        } else {
             uint64_t tg = tile_g;
             int b = (int)n_local - 1;
             while (tg) {
@@ -483,6 +547,22 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
         pp.ops = sel;
         cand.swap(rest);
         passes.push_back(pp);
+        if (h.remap) {
+            // the ops still to be scheduled see the new layout
+            const int gb = h.remap_g, lb = h.remap_b;
+            for (int idx : cand) {
+                POp &q = pl[idx];
+                q.d.a = swap_bits(q.d.a, gb, lb);
+                q.d.b = swap_bits(q.d.b, gb, lb);
+                q.d.ctrl = swap_bits(q.d.ctrl, gb, lb);
+                q.mix = swap_bits(q.mix, gb, lb);
+                q.dg = swap_bits(q.dg, gb, lb);
+            }
+            for (uint32_t q = 0; q < c.q_num; ++q) {
+                if (plan.perm[q] == gb) plan.perm[q] = (uint8_t)lb;
+                else if (plan.perm[q] == lb) plan.perm[q] = (uint8_t)gb;
+            }
+        }
     }
 
     // ---- stages of every tile pass ----
@@ -514,6 +594,8 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
             k = e;
         }
         h.fx_val = h.fx.val;
+        for (uint32_t l = 0; l < 16; ++l)
+            h.gpos_store[l] = (h.remap && l < h.T && h.gpos[l] == h.remap_g) ? h.remap_b : h.gpos[l];
         h.fixed_mask = 0;
         for (uint32_t k = 0; k < h.fx.n; ++k) h.fixed_mask |= 1ull << h.fx.pos[k];
 
@@ -531,11 +613,14 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                 cur.hdr.stage_end[k] = (uint16_t)(plan.stages[cur.hdr.stage_begin + k].op_end - cur.hdr.op_begin);
             cur.hdr.need_flags = 0;
             for (uint32_t k = 0; k < cur.hdr.n_ops; ++k) {
-                plan.mops[cur.hdr.op_begin + k].idx = (uint16_t)k;
+                MOp &mk = plan.mops[cur.hdr.op_begin + k];
+                mk.idx = (uint16_t)k;
+                if (!cur.hdr.full && mk.code < (uint8_t)FC_TOTAL)      // control class into the code byte (engine.h)
+                    mk.code = (uint8_t)(mk.code + FC_TOTAL * ((mk.dagger & MOP_CONDB) ? 2 : (mk.dagger & MOP_COND) ? 1 : 0));
                 const MBase &mb = plan.bases[cur.hdr.op_begin + k];
                 if (mb.ctrl_base | mb.a_base) cur.hdr.need_flags = 1;
             }
-            if (cur.hdr.n_ops) out_passes.push_back(cur);
+            if (cur.hdr.n_ops || (cur.hdr.remap && cur.hdr.n_stages)) out_passes.push_back(cur);
             cur.ops.clear();
             cur.hdr.stage_begin = (uint32_t)plan.stages.size();
             cur.hdr.op_begin = (uint32_t)plan.mops.size();
@@ -616,6 +701,7 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
             st.op_begin = (uint32_t)plan.mops.size();
             for (const StageSel &ss : s2) {
                 const POp &p = pl[ss.idx];
+                if (p.d.kind == QVNT_ID) continue;
                 MOp m;
                 MBase b;
                 MInfo mi;
@@ -634,7 +720,7 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                 mi.ra = ss.ra;
                 mi.rb = ss.rb;
                 if (pass_fast) {
-                    const double c = p.d.ph_re, sn = p.d.ph_im, h = QV_FRAC_1_SQRT_2;
+                    const double c = p.d.ph_re, sn = p.d.ph_im, hs = QV_FRAC_1_SQRT_2;
                     const bool dg = p.d.dagger != 0;
                     double f0r = 1.0, f0i = 0.0, f1r = 1.0, f1i = 0.0;
                     mi.form = p.cls == CLS_DIAG ? TF_DIAG : TF_PAIR1;
@@ -659,13 +745,36 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                             m.code = (uint8_t)FC_LX;
                             st.sync_after_load = 1;
                             m.a_thr = tthr;
-                            m.a_reg = (uint16_t)(lpos_of[ctz64(p.d.a)] | (ctz64(p.d.a) << 8));
+                            {
+                                const int pos = ctz64(p.d.a);
+                                m.a_reg = (uint16_t)(lpos_of[pos] | (((h.remap && pos == h.remap_g) ? h.remap_b : pos) << 8));
+                            }
+                            {
+                                // payload in the coefficient words (both blocks): byte distance of the bit in
+                                // the padded-linear tile buffer | the bit << 32, and its byte distance in the shard
+                                const uint32_t lp = (uint32_t)lpos_of[ctz64(p.d.a)], bit = 1u << lp;
+                                const uint64_t w = (uint64_t)(16u * (bit + (bit >> h.L))) | ((uint64_t)bit << 32);
+                                const int pos = ctz64(p.d.a);       // (a remap pass stores the rank bit at the pinned bit)
+                                const uint64_t g = 16ull << ((h.remap && pos == h.remap_g) ? h.remap_b : pos);
+                                const uint64_t at = (uint64_t)tthr;              // the target's thread bit
+                                memcpy(&m.ph_re, &w, 8);
+                                memcpy(&m.ph_im, &g, 8);
+                                memcpy(&m.c2, &at, 8);
+                                m.alt[0] = m.ph_re;
+                                m.alt[1] = m.ph_im;
+                                m.alt[2] = m.c2;
+                            }
                             mi.form = TF_LAZYX;
                             mi.ra = mi.rb = 0;
                         } else if (creg == 0) {
                             // no control in a register slot: the thread marks the slot as inverted
                             m.code = (uint8_t)FC_LI;
                             m.a_reg = (uint16_t)ss.ra;
+                            {
+                                const uint64_t w = (uint64_t)MOP_ALT_BYTES << (8 * ss.ra);   // the slot's inversion byte
+                                memcpy(&m.ph_re, &w, 8);
+                                m.alt[0] = m.ph_re;
+                            }
                             mi.form = TF_LAZYI;
                         } else {
                             m.code = (uint8_t)(FC_SW + ss.ra);
@@ -673,7 +782,7 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                         break;
                     case QVNT_Z: f1r = -1.0; break;
                     case QVNT_S: f1r = 0.0; f1i = dg ? -1.0 : 1.0; break;
-                    case QVNT_T: f1r = h; f1i = dg ? -h : h; break;
+                    case QVNT_T: f1r = hs; f1i = dg ? -hs : hs; break;
                     default: f0r = c; f0i = -sn; f1r = c; f1i = sn; break;      // rz, rzz
                     }
                     if (p.cls == CLS_DIAG) {
@@ -685,13 +794,18 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
                                  : pc64(areg) == 1 ? (uint8_t)(FC_DS + ctz64(areg)) : (uint8_t)FC_DG;
                         m.ph_re = f0r; m.ph_im = f0i; m.c2 = f1r; m.c3 = f1i;
                         m.alt[0] = f1r; m.alt[1] = f1i; m.alt[2] = f0r; m.alt[3] = f0i;
+                        if (m.code == (uint8_t)FC_DG) {      // per-slot-pattern factors: no role exchange, always the masked arm
+                            m.alt[0] = f0r; m.alt[1] = f0i; m.alt[2] = f1r; m.alt[3] = f1i;
+                            m.code = (uint8_t)(FC_DG + FC_MASKED);
+                        }
                         if (f0r == 1.0 && f0i == 0.0) m.dagger |= MOP_SKIP0;
                         if (b.a_base) m.dagger |= MOP_PARB;
+                        if (athr) m.dagger |= MOP_ATHR;
                         mi.ra = mi.rb = 0;
                     }
                     if (cthr || b.ctrl_base) m.dagger |= MOP_COND;
                     if (b.ctrl_base) m.dagger |= MOP_CONDB;
-                    if (m.okmask != 0xFFFFu && m.code < (uint8_t)FC_SW) m.code = (uint8_t)(m.code + FC_MASKED);
+                    if (m.okmask != 0xFFFFu && m.code < (uint8_t)FC_MASKED) m.code = (uint8_t)(m.code + FC_MASKED);
                 } else if (p.cls == CLS_DIAG) {
                     uint32_t areg, athr;
                     split(p.d.a, areg, athr, b.a_base);
@@ -806,74 +920,86 @@ static int build_plan(const PlanCfg &c, const std::vector<POp> &pl, Plan &plan) 
     return QVNT_OK;
 }
 
-static int run_plan(qvnt_reg *r, const std::vector<POp> &pl, Plan &plan) {
-    const uint32_t n_local = r->n_local;
-    // ---- upload the pass programs (one H2D copy from pinned staging) ----
+struct Uploaded {
     TStage *d_stages = nullptr;
     MOp *d_mops = nullptr;
     MBase *d_bases = nullptr;
-    if (!plan.stages.empty()) {
-        const size_t sb = plan.stages.size() * sizeof(TStage), ob = plan.mops.size() * sizeof(MOp),
-                     bb = plan.bases.size() * sizeof(MBase);
-        const size_t sb_al = (sb + 255) & ~(size_t)255, ob_al = (ob + 255) & ~(size_t)255;
-        const size_t total = sb_al + ob_al + bb;
-        int rc = ensure_stage(r, total);
-        if (rc) return rc;
-        if ((rc = ensure_dev(&r->d_ops, &r->d_ops_cap, total))) return rc;
-        memcpy(r->h_stage, plan.stages.data(), sb);
-        memcpy((char *)r->h_stage + sb_al, plan.mops.data(), ob);
-        memcpy((char *)r->h_stage + sb_al + ob_al, plan.bases.data(), bb);
-        QV_CUDA(cudaMemcpyAsync(r->d_ops, r->h_stage, total, cudaMemcpyHostToDevice, r->stream));
-        QV_CUDA(cudaEventRecord(r->stage_free, r->stream));
-        r->stage_busy = true;
-        r->stats.h2d_bytes += total;
-        d_stages = (TStage *)r->d_ops;
-        d_mops = (MOp *)((char *)r->d_ops + sb_al);
-        d_bases = (MBase *)((char *)r->d_ops + sb_al + ob_al);
-    }
+};
 
-    // ---- enqueue ----
-    bool need_barrier = false;      // peers may still be writing into / reading from this shard
-    for (PassPlan &pp : plan.passes) {
-        if (pp.direct) {
-            if (need_barrier) {
-                int rc = dist_barrier(r);
-                if (rc) return rc;
-                need_barrier = false;
-            }
-            int rc = run_direct(r, pl[pp.ops[0]]);
-            if (rc) return rc;
-            continue;
-        }
-        const TPassHdr &h = pp.hdr;
-        if (h.touches_peer || need_barrier) {
+// the pass programs of a plan -> device (one H2D copy from pinned staging)
+static int upload_plan(qvnt_reg *r, const Plan &plan, Uploaded &u) {
+    if (plan.stages.empty()) return QVNT_OK;
+    const size_t sb = plan.stages.size() * sizeof(TStage), ob = plan.mops.size() * sizeof(MOp),
+                 bb = plan.bases.size() * sizeof(MBase);
+    const size_t sb_al = (sb + 255) & ~(size_t)255, ob_al = (ob + 255) & ~(size_t)255;
+    const size_t total = sb_al + ob_al + bb;
+    int rc = ensure_stage(r, total);
+    if (rc) return rc;
+    if ((rc = ensure_dev(&r->d_ops, &r->d_ops_cap, total))) return rc;
+    memcpy(r->h_stage, plan.stages.data(), sb);
+    if (ob) memcpy((char *)r->h_stage + sb_al, plan.mops.data(), ob);
+    if (bb) memcpy((char *)r->h_stage + sb_al + ob_al, plan.bases.data(), bb);
+    QV_CUDA(cudaMemcpyAsync(r->d_ops, r->h_stage, total, cudaMemcpyHostToDevice, r->stream));
+    QV_CUDA(cudaEventRecord(r->stage_free, r->stream));
+    r->stage_busy = true;
+    r->stats.h2d_bytes += total;
+    u.d_stages = (TStage *)r->d_ops;
+    u.d_mops = (MOp *)((char *)r->d_ops + sb_al);
+    u.d_bases = (MBase *)((char *)r->d_ops + sb_al + ob_al);
+    return QVNT_OK;
+}
+
+// one pass of a plan, with the cross-GPU barriers it needs (need_barrier: peers may still be
+// writing into / reading from this shard)
+static int enqueue_pass(qvnt_reg *r, const std::vector<POp> &pl, const PassPlan &pp, const Uploaded &u,
+                        bool &need_barrier) {
+    const uint32_t n_local = r->n_local;
+    if (pp.direct) {
+        if (need_barrier) {
             int rc = dist_barrier(r);
             if (rc) return rc;
+            need_barrier = false;
         }
-        need_barrier = h.touches_peer != 0;
-        LaunchScope ls(r, 1);
-        int n = launch_tile_pass(r->stream, r->segs, h, d_stages, d_mops, d_bases, r->d_mat, r->sm_count, r->knobs);
-        ls.done(n);
-        if (n < 0) {
-            cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess) return cuda_fail(e, "tile pass launch");
-            set_error("internal: tile pass rejected (T=%u L=%u)", h.T, h.L);
-            return QVNT_ERR_INVALID;
-        }
-        r->stats.passes += 1;
-        r->stats.h2d_bytes += sizeof(TPassHdr) + sizeof(Segs);    // kernel parameters
-        const uint64_t amps = h.n_tiles << h.T;
-        r->stats.alg_bytes[1] += amps * 32;
-        if (h.touches_peer) {
-            int kg = 0;
-            for (uint32_t l = 0; l < h.T; ++l) kg += h.gpos[l] >= n_local;
-            r->stats.peer_bytes += ((amps * 32) >> kg) * ((1ull << kg) - 1ull);
-        }
+        return run_direct(r, pl[pp.ops[0]]);
     }
-    if (need_barrier) {
+    const TPassHdr &h = pp.hdr;
+    if (h.touches_peer || need_barrier) {
         int rc = dist_barrier(r);
         if (rc) return rc;
     }
+    // (a remap pass writes only this shard, and only places the peer has acknowledged reading)
+    need_barrier = h.touches_peer != 0 && !h.remap;
+    TPassHdr hl = h;
+    if (h.remap) hl.epoch = ++r->remap_epoch;
+    LaunchScope ls(r, 1);
+    int n = launch_tile_pass(r->stream, r->segs, hl, u.d_stages, u.d_mops, u.d_bases, r->d_mat, r->sm_count, r->knobs);
+    ls.done(n);
+    if (n < 0) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "tile pass launch");
+        set_error("internal: tile pass rejected (T=%u L=%u)", h.T, h.L);
+        return QVNT_ERR_INVALID;
+    }
+    r->stats.passes += 1;
+    r->stats.h2d_bytes += sizeof(TPassHdr) + sizeof(Segs);    // kernel parameters
+    const uint64_t amps = h.n_tiles << h.T;
+    r->stats.alg_bytes[1] += amps * 32;
+    if (h.touches_peer) {
+        int kg = 0;
+        for (uint32_t l = 0; l < h.T; ++l) kg += h.gpos[l] >= n_local;
+        r->stats.peer_bytes += h.remap ? amps * 8 : ((amps * 32) >> kg) * ((1ull << kg) - 1ull);
+    }
+    return QVNT_OK;
+}
+
+static int run_plan(qvnt_reg *r, const std::vector<POp> &pl, Plan &plan) {
+    Uploaded u;
+    int rc = upload_plan(r, plan, u);
+    if (rc) return rc;
+    bool need_barrier = false;
+    for (const PassPlan &pp : plan.passes)
+        if ((rc = enqueue_pass(r, pl, pp, u, need_barrier))) return rc;
+    if (need_barrier) return dist_barrier(r);
     return QVNT_OK;
 }
 
@@ -887,6 +1013,9 @@ static PlanCfg cfg_of(const qvnt_reg *r) {
     c.fuse = r->opt_fuse != 0;
     c.tile_bits = r->opt_tile_bits;
     c.chunk_bits = r->opt_chunk_bits;
+    c.remap = r->opt_remap != 0 && r->remap_possible;
+    c.ack_cap = r->ack_cap;
+    memcpy(c.perm, r->perm, sizeof(c.perm));
     return c;
 }
 
@@ -909,7 +1038,176 @@ int run_ops(qvnt_reg *r, const qvnt_op_t *ops, size_t n_ops) {
         QV_CUDA(cudaMemcpyAsync(r->d_mat, mats.data(), bytes, cudaMemcpyHostToDevice, r->stream));
         r->stats.h2d_bytes += bytes;
     }
+    if ((rc = run_plan(r, pl, plan))) return rc;
+    memcpy(r->perm, plan.perm, sizeof(r->perm));
+    return QVNT_OK;
+}
+
+// One remap pass that carries no gate: index bits g (global) and b (local) trade places.
+static int empty_remap_pass(qvnt_reg *r, const PlanCfg &base, uint32_t g, uint32_t b) {
+    PlanCfg c = base;
+    c.remap = true;
+    c.fuse = true;
+    c.force_pinned = (int)b;
+    std::vector<POp> pl(1);
+    memset(&pl[0], 0, sizeof(POp));
+    pl[0].d.kind = QVNT_ID;
+    pl[0].cls = CLS_PAIR;
+    pl[0].mix = 1ull << g;
+    pl[0].d.a = pl[0].la = 1ull << g;
+    Plan plan;
+    int rc = build_plan(c, pl, plan);
+    if (rc) return rc;
+    if (plan.passes.size() != 1 || !plan.passes[0].hdr.remap) {
+        set_error("internal: could not build the remap pass that restores qubit order (bits %u, %u)", g, b);
+        return QVNT_ERR_UNSUPPORTED;
+    }
     return run_plan(r, pl, plan);
+}
+
+// Undo the qubit remapping of earlier qvnt_reg_apply calls: every API that addresses amplitudes by
+// index (read / write / probabilities / measurement order / collapse) expects qubit q at index bit q.
+// Global bits first -- one EMPTY remap pass each (data movement only: the pinned bit is the local bit
+// that holds the qubit belonging to the global position); what is left is a permutation of local
+// bits, undone by swap gates on the index bits (pure permutations: exact).
+int restore_layout(qvnt_reg *g) {
+    // (a group handle restores all its shards in step; they share one qubit map)
+    qvnt_reg *r = g->shards.empty() ? g : g->shards[0];
+    bool ident = true;
+    for (uint32_t q = 0; q < r->q_num; ++q) ident = ident && r->perm[q] == q;
+    if (ident) return QVNT_OK;
+    PlanCfg c = cfg_of(r);
+    for (uint32_t q = 0; q < 64; ++q) c.perm[q] = (uint8_t)q;       // the passes below are built in PHYSICAL numbering
+    uint8_t at[64];                                                  // at[p] = qubit at index bit p
+    for (uint32_t q = 0; q < r->q_num; ++q) at[r->perm[q]] = (uint8_t)q;
+    std::vector<POp> pl;
+    Plan plan;
+    memcpy(plan.perm, c.perm, sizeof(plan.perm));
+    auto swap_pos = [&](uint32_t a, uint32_t b) {
+        const uint8_t qa = at[a], qb = at[b];
+        at[a] = qb;
+        at[b] = qa;
+        r->perm[qa] = (uint8_t)b;
+        r->perm[qb] = (uint8_t)a;
+        for (qvnt_reg *s : g->shards) memcpy(s->perm, r->perm, sizeof(r->perm));
+    };
+    auto empty_pass = [&](uint32_t gb, uint32_t lb) -> int {
+        if (g->shards.empty()) return empty_remap_pass(r, c, gb, lb);
+        for (qvnt_reg *s : g->shards) {
+            QV_CUDA(cudaSetDevice(s->device));
+            PlanCfg cs = cfg_of(s);
+            memcpy(cs.perm, c.perm, sizeof(cs.perm));
+            int rc = empty_remap_pass(s, cs, gb, lb);
+            if (rc) return rc;
+        }
+        return QVNT_OK;
+    };
+    // 1. global positions
+    for (uint32_t gp = r->n_local; gp < r->q_num; ++gp) {
+        while (at[gp] != gp) {
+            uint32_t p = r->perm[gp];                // where the qubit that belongs at gp sits now
+            if (p >= r->n_local) {
+                // it sits at ANOTHER global position: bring it to a local bit first
+                uint32_t b = r->n_local - 1;
+                int rc = empty_pass(p, b);
+                if (rc) return rc;
+                swap_pos(p, b);
+                continue;
+            }
+            int rc = empty_pass(gp, p);
+            if (rc) return rc;
+            swap_pos(gp, p);
+        }
+    }
+    // 2. local positions: cycle decomposition into swaps of index bits
+    std::vector<qvnt_op_t> sw;
+    for (uint32_t p = 0; p < r->n_local; ++p) {
+        while (at[p] != p) {
+            const uint32_t q = r->perm[p];           // qubit p sits at index bit q
+            qvnt_op_t o;
+            memset(&o, 0, sizeof(o));
+            o.kind = QVNT_SWAP;
+            o.a_mask = (1ull << p) | (1ull << q);
+            sw.push_back(o);
+            swap_pos(p, q);
+        }
+    }
+    // (perm is the identity now, so run_ops plans these swaps in plain index-bit numbering)
+    if (!sw.empty()) {
+        const int keep = r->opt_remap;
+        const uint64_t ops_before = r->stats.ops_applied;
+        r->opt_remap = 0;
+        for (qvnt_reg *s : g->shards) s->opt_remap = 0;
+        int rc = g->shards.empty() ? run_ops(r, sw.data(), sw.size()) : run_ops_group(g, sw.data(), sw.size());
+        r->stats.ops_applied = ops_before;
+        r->opt_remap = keep;
+        for (qvnt_reg *s : g->shards) s->opt_remap = keep;
+        if (rc) return rc;
+    }
+    return QVNT_OK;
+}
+
+// ---- group handles: one host thread drives every shard -----------------------------------------
+// Pass k of every shard is enqueued before pass k + 1 of any: a shard's barrier kernel spins until
+// the other shards' barrier kernels run, so no shard may get a whole plan ahead of the others (a
+// full launch queue would block the host with the peers' kernels not yet enqueued).
+static int run_plans_group(qvnt_reg *g, std::vector<std::vector<POp>> &pls, std::vector<Plan> &plans) {
+    const size_t P = g->shards.size();
+    std::vector<Uploaded> ups(P);
+    for (size_t k = 0; k < P; ++k) {
+        if (plans[k].passes.size() != plans[0].passes.size()) {
+            set_error("internal: shards planned different pass counts");
+            return QVNT_ERR_INVALID;
+        }
+        QV_CUDA(cudaSetDevice(g->shards[k]->device));
+        int rc = upload_plan(g->shards[k], plans[k], ups[k]);
+        if (rc) return rc;
+    }
+    std::vector<char> need(P, 0);
+    for (size_t i = 0; i < plans[0].passes.size(); ++i)
+        for (size_t k = 0; k < P; ++k) {
+            QV_CUDA(cudaSetDevice(g->shards[k]->device));
+            bool nb = need[k] != 0;
+            int rc = enqueue_pass(g->shards[k], pls[k], plans[k].passes[i], ups[k], nb);
+            need[k] = nb;
+            if (rc) return rc;
+        }
+    for (size_t k = 0; k < P; ++k)
+        if (need[k]) {
+            QV_CUDA(cudaSetDevice(g->shards[k]->device));
+            int rc = dist_barrier(g->shards[k]);
+            if (rc) return rc;
+        }
+    return QVNT_OK;
+}
+
+int run_ops_group(qvnt_reg *g, const qvnt_op_t *ops, size_t n_ops) {
+    const size_t P = g->shards.size();
+    std::vector<std::vector<POp>> pls(P);
+    std::vector<Plan> plans(P);
+    for (size_t k = 0; k < P; ++k) {
+        qvnt_reg *r = g->shards[k];
+        std::vector<amp> mats;
+        const PlanCfg c = cfg_of(r);
+        int rc = lower_ops(c, ops, n_ops, pls[k], mats);
+        if (rc) return rc;
+        r->stats.ops_applied += k == 0 ? n_ops : 0;
+        if (pls[k].empty()) continue;
+        if ((rc = build_plan(c, pls[k], plans[k]))) return rc;
+        if (!mats.empty()) {
+            QV_CUDA(cudaSetDevice(r->device));
+            const size_t bytes = mats.size() * sizeof(amp);
+            if ((rc = ensure_dev((void **)&r->d_mat, &r->d_mat_cap, bytes))) return rc;
+            QV_CUDA(cudaMemcpyAsync(r->d_mat, mats.data(), bytes, cudaMemcpyHostToDevice, r->stream));
+            QV_CUDA(cudaStreamSynchronize(r->stream));       // (mats is a local)
+            r->stats.h2d_bytes += bytes;
+        }
+    }
+    if (pls[0].empty()) return QVNT_OK;
+    int rc = run_plans_group(g, pls, plans);
+    if (rc) return rc;
+    for (size_t k = 0; k < P; ++k) memcpy(g->shards[k]->perm, plans[k].perm, sizeof(plans[k].perm));
+    return QVNT_OK;
 }
 
 // Text dump of the schedule (tests, DESIGN.md, debugging); needs no device.
@@ -927,6 +1225,8 @@ int describe_plan(uint32_t q_num, uint32_t rank, uint32_t world, int peers, int 
     }
     c.n_local = q_num - wb;
     c.peers = peers != 0;
+    c.remap = !(peers & 2);          // (peers_attached == 3: peers attached, remap passes off)
+    for (uint32_t q = 0; q < 64; ++q) c.perm[q] = (uint8_t)q;
     c.fuse = fuse != 0;
     c.tile_bits = tile_bits;
     c.chunk_bits = chunk_bits;
@@ -939,8 +1239,13 @@ int describe_plan(uint32_t q_num, uint32_t rank, uint32_t world, int peers, int 
     char buf[1024];
     auto op_line = [&](const POp &p, int form, int ra, int rb) {
         // scale: the butterfly factor of an h1 (1/sqrt2; the halves of a split h2 carry 1 and 0.5)
-        snprintf(buf, sizeof(buf), "op src=%u kind=%u dagger=%u a=%llu b=%llu ctrl=%llu form=%d ra=%d rb=%d scale=%a\n",
-                 p.src, p.d.kind, p.d.dagger, (unsigned long long)p.d.a, (unsigned long long)p.d.b,
+        // a / b / ctrl: LOGICAL (qubit) masks as the caller gave them; pa / pb / pctrl: the index bits they
+        // occupied when the op was scheduled (differ after a remap pass)
+        snprintf(buf, sizeof(buf),
+                 "op src=%u kind=%u dagger=%u a=%llu b=%llu ctrl=%llu pa=%llu pb=%llu pctrl=%llu form=%d ra=%d rb=%d "
+                 "scale=%a\n",
+                 p.src, p.d.kind, p.d.dagger, (unsigned long long)p.la, (unsigned long long)p.lb,
+                 (unsigned long long)p.lctrl, (unsigned long long)p.d.a, (unsigned long long)p.d.b,
                  (unsigned long long)p.d.ctrl, form, ra, rb, p.d.kind == QVNT_H1 ? p.d.ph_re : 0.0);
         out += buf;
     };
@@ -951,9 +1256,10 @@ int describe_plan(uint32_t q_num, uint32_t rank, uint32_t world, int peers, int 
             continue;
         }
         const TPassHdr &h = pp.hdr;
-        snprintf(buf, sizeof(buf), "pass tile T=%u L=%u n_tiles=%llu base_or=%llu peer=%u full=%u fx_val=%llu gpos=",
+        snprintf(buf, sizeof(buf),
+                 "pass tile T=%u L=%u n_tiles=%llu base_or=%llu peer=%u full=%u fx_val=%llu remap=%u rg=%u rb=%u gpos=",
                  h.T, h.L, (unsigned long long)h.n_tiles, (unsigned long long)h.base_or, h.touches_peer, h.full,
-                 (unsigned long long)h.fx.val);
+                 (unsigned long long)h.fx.val, h.remap, h.remap_g, h.remap_b);
         out += buf;
         for (uint32_t l = 0; l < h.T; ++l) out += std::to_string(h.gpos[l]) + (l + 1 < h.T ? "," : "");
         out += " fx_pos=";

@@ -25,6 +25,15 @@ struct qvnt_reg {
     unsigned long long *mail[qv::MAX_WORLD] = {};
     uint64_t barrier_epoch = 0;
     uint64_t gather_epoch = 0;
+    // qubit remapping (sharded registers): logical qubit q lives at index bit perm[q]; identity until a
+    // remap pass of qvnt_reg_apply trades a global for a local bit, restored lazily (restore_layout)
+    uint8_t perm[64];
+    unsigned int *ack = nullptr;            // per-tile handshake words of remap passes (IPC-shared)
+    uint64_t ack_cap = 0;                   // entries
+    void *peer_ack[qv::MAX_WORLD] = {};
+    uint32_t remap_epoch = 0;
+    int opt_remap = 1;
+    bool remap_possible = false;            // one GPU per shard (set by attach_peers)
 
     // scratch (device)
     double *d_partials = nullptr;   // REDUCE_BLOCKS_MAX
@@ -44,6 +53,10 @@ struct qvnt_reg {
     cudaEvent_t stage_free = nullptr;  // recorded after the last H2D copy out of h_stage
     bool stage_busy = false;
     double *h_scalars = nullptr;    // pinned, 32 doubles / words
+
+    // A GROUP handle (qvnt_reg_create_multi): one host process drives every shard; the group owns no
+    // device memory itself.  Every C-ABI entry point dispatches on shards.empty().
+    std::vector<qvnt_reg *> shards;
 
     // options
     int opt_fuse = 1;
@@ -84,6 +97,10 @@ struct LaunchScope {
 
 // planner.cu: validate + schedule + enqueue one op list
 int run_ops(qvnt_reg *r, const qvnt_op_t *ops, size_t n_ops);
+// the same for all shards of a group handle: every shard's pass k is enqueued before any pass k + 1
+int run_ops_group(qvnt_reg *g, const qvnt_op_t *ops, size_t n_ops);
+// puts the qubits back at their own index bits (no-op while perm is the identity)
+int restore_layout(qvnt_reg *r);
 int describe_plan(uint32_t q_num, uint32_t rank, uint32_t world, int peers, int fuse, int tile_bits,
                   int chunk_bits, const qvnt_op_t *ops, size_t n_ops, std::string &out);
 // multi-GPU plumbing (dist.cu)

@@ -56,6 +56,7 @@
 #include <mutex>
 
 #include "engine.h"
+#include "fastops_ptx.inc"
 #include "gates.cuh"
 
 namespace qv {
@@ -586,7 +587,7 @@ __device__ __forceinline__ void stage_ops_fast(const unsigned char *ops, const v
         const unsigned char *const op = p;
         const uint4 h = *reinterpret_cast<const uint4 *>(op);     // w0 | ctrl_thr | a_thr | a_reg + idx << 16
         p += MOP_BYTES;
-        uint32_t code = h.x & 0xFFu;
+        uint32_t code = (h.x & 0xFFu) % (uint32_t)FC_TOTAL;       // (the byte also carries the control class)
         if (h.x & ((uint32_t)MOP_COND << 8)) {
             bool skip = (~vgrp & h.y) != 0u;
             if (h.x & ((uint32_t)MOP_CONDB << 8)) skip = skip || !(flags[h.w >> 16] & 0x80u);
@@ -653,6 +654,27 @@ __device__ __forceinline__ void stage_ops_fast(const unsigned char *ops, const v
     }
 }
 
+// The same op loop as ONE inline-PTX block (gen_fastops.py -> fastops_ptx.inc): header fetch,
+// control test, a single brx.idx jump table and every arm.  The C++ loop above compiles to a
+// compare tree plus divergence bookkeeping (~40 instructions and several dependent branches per op);
+// this one spends ~20.  Option "ptx_ops" (default 1) selects it; the C++ loop stays as the readable
+// specification and the A/B baseline.
+__device__ __forceinline__ void stage_ops_fast_ptx(const uint32_t ops_s, const uint32_t flags_s, const uint32_t ob,
+                                                   const uint32_t oe, const uint32_t grp, StageCtx &x, uint32_t &inv,
+                                                   amp (&v)[NV]) {
+    uint32_t vgrp = grp;
+    const uint32_t pb = ops_s + MOP_BYTES * ob, pe = ops_s + MOP_BYTES * oe;
+    asm volatile(QV_FASTOPS_PTX
+                 : "+d"(v[0].x), "+d"(v[0].y), "+d"(v[1].x), "+d"(v[1].y), "+d"(v[2].x), "+d"(v[2].y), "+d"(v[3].x),
+                   "+d"(v[3].y), "+d"(v[4].x), "+d"(v[4].y), "+d"(v[5].x), "+d"(v[5].y), "+d"(v[6].x), "+d"(v[6].y),
+                   "+d"(v[7].x), "+d"(v[7].y), "+d"(v[8].x), "+d"(v[8].y), "+d"(v[9].x), "+d"(v[9].y), "+d"(v[10].x),
+                   "+d"(v[10].y), "+d"(v[11].x), "+d"(v[11].y), "+d"(v[12].x), "+d"(v[12].y), "+d"(v[13].x),
+                   "+d"(v[13].y), "+d"(v[14].x), "+d"(v[14].y), "+d"(v[15].x), "+d"(v[15].y), "+r"(vgrp), "+r"(inv),
+                   "+r"(x.jl), "+r"(x.mine_o), "+l"(x.goff)
+                 : "r"(pb), "r"(pe), "r"(flags_s)
+                 : "memory");
+}
+
 // ---- TMA bulk copy + mbarrier (tile loads) -------------------------------------------------------
 __device__ __forceinline__ void mbar_init(const uint32_t mbar, const uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(mbar), "r"(count) : "memory");
@@ -685,14 +707,14 @@ __device__ __forceinline__ void bulk_prefetch_l2(const unsigned long long src, c
 
 // Kernel configurations: <threads per CTA, min CTAs per SM>.
 //   T == 12: 256 threads, 2 CTAs/SM, one 68 KiB buffer.
-//   T <= 11: 128 threads, 4 CTAs/SM, one 34 KiB buffer each (default; option "tile_ctas" 3 / 5).
+//   T <= 11: 128 threads, 4 CTAs/SM, one 34 KiB buffer each (default; option "tile_ctas" 3).
 // One buffer per CTA: the last stage stores its registers straight to HBM, so the buffer is free
 // as soon as that stage has read it -- the next tile's load is issued right there and overlaps
 // the last stage's arithmetic and stores.
 constexpr uint32_t META_SLOTS = 3;      // per-tile op flags rotate through 3 slots: preparing tile i+1 must not
                                         // race with the threads still running the ops of tile i-1
 
-template <int THREADS, int MINB, bool FULL, bool BULK>
+template <int THREADS, int MINB, bool FULL, bool BULK, bool PTXOPS, bool DB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr hdr,
             const TStage *__restrict__ g_stages, const MOp *__restrict__ g_ops,
@@ -709,17 +731,18 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     const uint32_t flags_stride = (n_ops + 15u) & ~15u;
 
     // shared memory carve-up (16-byte aligned sections first)
-    unsigned char *tile_b = smem_raw;                                              // n_chunks * (16 * 2^L + 16)
-    unsigned long long *s_mbar = reinterpret_cast<unsigned long long *>(smem_raw + buf_bytes);   // 16
-    MOp *s_ops = reinterpret_cast<MOp *>(smem_raw + buf_bytes + 16u);              // 80 * n_ops
+    unsigned char *tile_b = smem_raw;                                              // (DB ? 2 : 1) * n_chunks * (16 * 2^L + 16)
+    const uint32_t bufs_bytes = DB ? 2u * buf_bytes : buf_bytes;
+    unsigned long long *s_mbar = reinterpret_cast<unsigned long long *>(smem_raw + bufs_bytes);   // 16
+    MOp *s_ops = reinterpret_cast<MOp *>(smem_raw + bufs_bytes + 16u);             // 80 * n_ops
     TStage *s_stages = reinterpret_cast<TStage *>(s_ops + n_ops);                  // 32 * n_stages
     MBase *s_bases = reinterpret_cast<MBase *>(s_stages + n_stages);               // 16 * n_ops
-    unsigned long long *s_ptr0 = reinterpret_cast<unsigned long long *>(s_bases + n_ops);   // 8 * n_chunks
-    unsigned long long *s_goff = s_ptr0 + ((n_chunks + 1u) & ~1u);                 // 8 * nthr (last stage)
-    uint4 *s_ctab = reinterpret_cast<uint4 *>(s_goff + nthr);                      // 16 * n_stages
+    const uint32_t n_bases = (FULL || hdr.need_flags) ? n_ops : 0u;                 // (per-tile flags only)
+    unsigned long long *s_ptr0 = reinterpret_cast<unsigned long long *>(s_bases + n_bases);   // 8 * n_chunks
+    uint4 *s_ctab = reinterpret_cast<uint4 *>(s_ptr0 + ((n_chunks + 1u) & ~1u));   // 16 * n_stages
     uint32_t *s_jltab = reinterpret_cast<uint32_t *>(s_ctab + n_stages);           // 4 * nthr * n_stages
     uint8_t *s_gpos = reinterpret_cast<uint8_t *>(s_jltab + nthr * n_stages);      // 16
-    uint8_t *s_flags_all = s_gpos + 16;                                            // 3 * flags_stride
+    uint8_t *s_flags_all = s_gpos + 16;                                            // 3 * flags_stride (need_flags)
 
     const uint32_t shard_shift = segs.shift;
     const uint64_t shard_mask = (1ull << shard_shift) - 1ull;
@@ -732,9 +755,11 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
         src = reinterpret_cast<const uint4 *>(g_stages + hdr.stage_begin);
         dst = reinterpret_cast<uint4 *>(s_stages);
         for (uint32_t i = tid; i < 2 * n_stages; i += nthr) dst[i] = src[i];
-        src = reinterpret_cast<const uint4 *>(g_bases + hdr.op_begin);
-        dst = reinterpret_cast<uint4 *>(s_bases);
-        for (uint32_t i = tid; i < n_ops; i += nthr) dst[i] = src[i];
+        if (FULL || hdr.need_flags) {
+            src = reinterpret_cast<const uint4 *>(g_bases + hdr.op_begin);
+            dst = reinterpret_cast<uint4 *>(s_bases);
+            for (uint32_t i = tid; i < n_ops; i += nthr) dst[i] = src[i];
+        }
         // Chunk base pointers for the tile at offset 0: chunk c = the 2^L amplitudes whose gathered
         // tile bits spell c.  Rank bits among them select the shard (own HBM or a peer's, mapped
         // over NVLink); every tile of the pass adds the same byte offset to all of them.
@@ -747,9 +772,10 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
         if (BULK && tid == 0) mbar_init(mbar, 1u);
     }
     const uint32_t n_t = T - TR;                     // thread bits per stage
-    if (tid < 16u) s_gpos[tid] = hdr.gpos[tid];
+    if (tid < 16u) s_gpos[tid] = hdr.gpos_store[tid];      // where the last stage stores each tile-local bit
     __syncthreads();                                 // the stage descriptors are in shared memory
     // per-(stage, thread) and per-stage constants, once per kernel
+    unsigned long long my_goff = 0;                  // last stage: byte offset of this thread's jl inside the tile's span
     for (uint32_t st = 0; st < n_stages; ++st) {
         const uint32_t jl = stage_jl(s_stages[st], n_t, tid);
         s_jltab[st * nthr + tid] = (slot16(jl, L) << 16) | jl;
@@ -758,17 +784,28 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
         if (st + 1 == n_stages) {
             unsigned long long go = 0;
             for (uint32_t l = 0; l < T; ++l)
-                if ((jl >> l) & 1u) go += 16ull << hdr.gpos[l];
-            s_goff[tid] = go;
+                if ((jl >> l) & 1u) go += 16ull << hdr.gpos_store[l];
+            my_goff = go;
         }
     }
-    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile_b);
+    const uint32_t tile_s0 = (uint32_t)__cvta_generic_to_shared(tile_b);
+    uint32_t tile_s = tile_s0;                       // the buffer of the tile being computed (DB: alternates)
     const unsigned long long shard_base = (unsigned long long)(uintptr_t)segs.seg[segs.rank];
     const uint32_t ops_s = (uint32_t)__cvta_generic_to_shared(s_ops);
     const uint32_t flags_all_s = (uint32_t)__cvta_generic_to_shared(s_flags_all);
     const uint32_t ptr0_s = (uint32_t)__cvta_generic_to_shared(s_ptr0);
     const bool active = tid < (1u << n_t);           // this thread owns a group of 16 amplitudes
     const bool need_flags = FULL || hdr.need_flags != 0u;
+    // Remap pass: the last stage writes both halves of the tile into THIS shard (the peer half at the
+    // pinned bit's other value), i.e. into the place the peer's CTA of the same tile loads ITS peer
+    // half from.  Handshake per tile: after its load has landed a CTA stores the pass's epoch into
+    // the peer's ack word of that tile; before its final stores it waits for its own ack word.  Both
+    // GPUs walk the tiles in the same order with the same grid, and a load never waits, so the wait
+    // always ends.
+    const bool remap = hdr.remap != 0u;
+    const unsigned long long store_keep = remap ? ~(16ull << hdr.remap_b) : ~0ull;
+    unsigned int *const ack_mine = segs.ack[segs.rank];
+    unsigned int *const ack_peer = remap ? segs.ack[segs.rank ^ (1u << (hdr.remap_g - segs.shift))] : nullptr;
     __syncthreads();
 
     // Tile counter -> local base index (tile bits and ownership bits clear): the counter's bits
@@ -803,6 +840,7 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
                 flags[o] = (uint8_t)(okb | ((uint32_t)__popcll(gb & b.a_base) & 7u));
                 any |= (int)okb;
             }
+            if (remap) any = 1;                          // every tile moves
             if (__syncthreads_or(any)) return;
         }
     };
@@ -812,7 +850,7 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     // !BULK: one 16-byte cp.async per amplitude; element j = tid + i * nthr, so with nthr a multiple
     // of the chunk length every iteration advances the chunk by nthr >> L and keeps the offset.
     const bool regular = (nthr & lmask) == 0u && (tile_len % nthr) == 0u;
-    auto issue_load = [&](const unsigned long long toff) {
+    auto issue_load = [&](const unsigned long long toff, const uint32_t tile_s) {
         if (BULK) {
             if ((tid & 31u) == 0u) {
                 if (tid == 0) {
@@ -846,12 +884,16 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     };
 
     // The CTA has ONE tile buffer, so the shared-memory load of tile i+1 cannot start before the last
-    // stage of tile i; to keep the HBM latency off that path the chunks of tile i+1 are prefetched
+    // stage of tile i; to keep the HBM latency off that path the lines of tile i+1 are prefetched
     // into L2 a whole tile earlier (hdr.prefetch), and the late load finds them there.
     auto prefetch_tile = [&](const unsigned long long toff) {
-        if ((tid & 31u) == 0u) {
-            const uint32_t nw = nthr >> 5;
-            for (uint32_t c = tid >> 5; c < n_chunks; c += nw) bulk_prefetch_l2(s_ptr0[c] + toff, chunk_bytes);
+        // one 128-byte line per thread and step: two instructions per 256 bytes, no registers held
+        const uint32_t lines_per_chunk = chunk_bytes >> 7;
+        if (lines_per_chunk == 0) return;
+        const uint32_t n_lines = n_chunks * lines_per_chunk, lsh = L - 3u;      // chunk = line >> (L - 3)
+        for (uint32_t ln = tid; ln < n_lines; ln += nthr) {
+            const unsigned long long p = s_ptr0[ln >> lsh] + toff + (unsigned long long)(ln & (lines_per_chunk - 1u)) * 128ull;
+            asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
         }
     };
 
@@ -859,7 +901,7 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     unsigned long long toff_cur = 0, toff_next = 0;
     uint64_t t_cur = blockIdx.x, base_cur = expand(blockIdx.x);
     prepare(t_cur, base_cur, mslot, toff_cur);
-    if (t_cur < hdr.n_tiles) issue_load(toff_cur);
+    if (t_cur < hdr.n_tiles) issue_load(toff_cur, tile_s);
     while (t_cur < hdr.n_tiles) {
         const uint32_t mnext = mslot + 1u == META_SLOTS ? 0u : mslot + 1u;
         uint64_t t_next = t_cur + gridDim.x, base_next = ((base_cur | fixed) + step) & ~fixed;
@@ -872,9 +914,16 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
         } else {
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             __syncthreads();
+            if (DB && has_next) {
+                // Two buffers: everybody is done with the previous tile (the barrier above), so its
+                // buffer takes the next tile NOW -- a whole tile of compute ahead of its use.
+                issue_load(toff_next, tile_s ^ tile_s0 ^ (tile_s0 + buf_bytes));
+            }
         }
         const uint8_t *flags = s_flags_all + mslot * flags_stride;
         const uint32_t flags_s = flags_all_s + mslot * flags_stride;
+        if (remap && tid == 0)       // "I have read your copy of tile t_cur"
+            asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(ack_peer + t_cur), "r"(hdr.epoch) : "memory");
         if (hdr.prefetch && has_next) prefetch_tile(toff_next);
 
         for (uint32_t s = 0; s < n_stages; ++s) {
@@ -884,12 +933,40 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
             StageCtx x;
             if (active) {
                 x = stage_ctx(s_stages + s, s_jltab + (s * nthr + tid), s_ctab + s);
-                if (last) x.goff = s_goff[tid];
+                if (last) x.goff = my_goff;
                 stage_load(tile_s, x, v);
             }
-            if (last) {
+            if (last && DB) {
+                if (remap) {
+                    if (tid == 0) {
+                        unsigned int got;
+                        unsigned long long spins = 0;
+                        do {
+                            asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(got) : "l"(ack_mine + t_cur) : "memory");
+                            if (got != hdr.epoch && ++spins > (1ull << 24)) {
+                                __nanosleep(1000);
+                                if (spins > (1ull << 24) + 20000000ull) __trap();
+                            }
+                        } while (got != hdr.epoch);
+                    }
+                    __syncthreads();
+                }
+            } else if (last) {
+                if (remap && tid == 0) {               // the peer has read what the stores below overwrite
+                    // (bounded: a peer kernel that never runs -- shards sharing a GPU, a dead peer -- must
+                    // surface as an error, not as a hung GPU)
+                    unsigned int got;
+                    unsigned long long spins = 0;
+                    do {
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(got) : "l"(ack_mine + t_cur) : "memory");
+                        if (got != hdr.epoch && ++spins > (1ull << 24)) {
+                            __nanosleep(1000);
+                            if (spins > (1ull << 24) + 20000000ull) __trap();      // ~20 s
+                        }
+                    } while (got != hdr.epoch);
+                }
                 __syncthreads();                       // every thread holds its amplitudes: the buffer is free
-                if (has_next) issue_load(toff_next);
+                if (has_next) issue_load(toff_next, tile_s);
             } else if (s_stages[s].sync_after_load) {
                 // a lazy x makes threads store into each other's slots of the tile buffer: nobody
                 // may store before everybody has loaded
@@ -898,14 +975,16 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
             if (active) {
                 uint32_t inv = 0;
                 if (FULL) stage_ops_full(ops_s, flags_s, ob, oe, tid, mats, v);
+                else if (PTXOPS) stage_ops_fast_ptx(ops_s, flags_s, ob, oe, tid, x, inv, v);
                 else stage_ops_fast(reinterpret_cast<const unsigned char *>(s_ops), flags, ob, oe, tid, L, x, inv, v);
                 if (!last) stage_store_smem(tile_s, x, inv, v);
-                else if (hdr.touches_peer) stage_store_global(ptr0_s, L, toff_cur, x, inv, v);
-                else stage_store_global_local(shard_base + toff_cur, s_gpos, x, inv, v);
+                else if (hdr.touches_peer && !remap) stage_store_global(ptr0_s, L, toff_cur, x, inv, v);
+                else stage_store_global_local(shard_base + (toff_cur & store_keep), s_gpos, x, inv, v);
             }
             if (!last) __syncthreads();
         }
         mslot = mnext;
+        if (DB) tile_s = tile_s ^ tile_s0 ^ (tile_s0 + buf_bytes);
         t_cur = t_next;
         base_cur = base_next;
         toff_cur = toff_next;
@@ -913,30 +992,34 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     // Stores into a peer's HBM must be performed at SYSTEM scope before the barrier kernel that
     // follows signals the peers: the barrier's own fence is executed by other threads and does not
     // cover them.
-    if (hdr.touches_peer) __threadfence_system();
+    if (hdr.touches_peer && !remap) __threadfence_system();
 }
 
 constexpr size_t TILE_SMEM_MAX = 227u * 1024u;
 
-static size_t tile_smem_bytes(const TPassHdr &h, int threads) {
-    return ((size_t)16 << h.T) + ((size_t)16 << (h.T - h.L)) + 16 + (size_t)(MOP_BYTES + sizeof(MBase)) * h.n_ops +
-           (size_t)32 * h.n_stages + (((size_t)8 << (h.T - h.L)) + 8) + (size_t)8 * threads + (size_t)16 * h.n_stages +
-           (size_t)4 * threads * h.n_stages + 16 + (size_t)META_SLOTS * ((h.n_ops + 15u) & ~15u);
+static size_t tile_smem_bytes(const TPassHdr &h, int threads, bool db = false) {
+    const bool flags = h.full || h.need_flags;
+    return (db ? 2 : 1) * (((size_t)16 << h.T) + ((size_t)16 << (h.T - h.L))) + 16 + (size_t)MOP_BYTES * h.n_ops +
+           (flags ? sizeof(MBase) * h.n_ops : 0) + (size_t)32 * h.n_stages + (((size_t)8 << (h.T - h.L)) + 8) +
+           (size_t)16 * h.n_stages + (size_t)4 * threads * h.n_stages + 16 +
+           (flags ? (size_t)META_SLOTS * ((h.n_ops + 15u) & ~15u) : 16);
 }
 
 typedef void (*tile_kernel_t)(const Segs, const TPassHdr, const TStage *, const MOp *, const MBase *, const amp *);
 
 template <int THREADS, int MINB>
-static tile_kernel_t pick_kernel(bool full, bool bulk) {
-    if (full) return bulk ? k_tile_pass<THREADS, MINB, true, true> : k_tile_pass<THREADS, MINB, true, false>;
-    return bulk ? k_tile_pass<THREADS, MINB, false, true> : k_tile_pass<THREADS, MINB, false, false>;
+static tile_kernel_t pick_kernel(bool full, bool bulk, bool ptx) {
+    if (full) return bulk ? k_tile_pass<THREADS, MINB, true, true, false, false> : k_tile_pass<THREADS, MINB, true, false, false, false>;
+    if (ptx) return bulk ? k_tile_pass<THREADS, MINB, false, true, true, false> : k_tile_pass<THREADS, MINB, false, false, true, false>;
+    return bulk ? k_tile_pass<THREADS, MINB, false, true, false, false> : k_tile_pass<THREADS, MINB, false, false, false, false>;
 }
 
-static tile_kernel_t select_kernel(int threads, int ctas, bool full, bool bulk) {
-    if (threads == 256) return pick_kernel<256, 2>(full, bulk);
-    if (ctas == 3) return pick_kernel<128, 3>(full, bulk);
-    if (ctas == 5) return pick_kernel<128, 5>(full, bulk);
-    return pick_kernel<128, 4>(full, bulk);
+static tile_kernel_t select_kernel(int threads, int ctas, bool full, bool bulk, bool ptx, bool db) {
+    // two tile buffers: the cp.async fast path with the PTX op loop, 3 CTAs of 128 threads per SM
+    if (db && threads == 128 && !full && !bulk && ptx) return k_tile_pass<128, 3, false, false, true, true>;
+    if (threads == 256) return pick_kernel<256, 2>(full, bulk, ptx);
+    if (ctas == 4) return pick_kernel<128, 4>(full, bulk, ptx);
+    return pick_kernel<128, 3>(full, bulk, ptx);
 }
 
 // cudaFuncSetAttribute is per device and costs a driver call per kernel: once per process and device.
@@ -950,11 +1033,12 @@ int tile_kernel_setup() {
     bool ok = true;
     for (int full = 0; full < 2; ++full)
         for (int bulk = 0; bulk < 2; ++bulk)
-            for (int cfg = 0; cfg < 4; ++cfg) {
-                const tile_kernel_t k = select_kernel(cfg == 0 ? 256 : 128, cfg == 1 ? 3 : cfg == 2 ? 5 : 4, full, bulk);
-                ok = ok && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)TILE_SMEM_MAX) == cudaSuccess;
-            }
+            for (int ptx = 0; ptx < 2; ++ptx)
+                for (int cfg = 0; cfg < 4; ++cfg) {
+                    const tile_kernel_t k = select_kernel(cfg == 0 ? 256 : 128, cfg == 1 ? 3 : 4, full, bulk, ptx, cfg == 3);
+                    ok = ok && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    (int)TILE_SMEM_MAX) == cudaSuccess;
+                }
     done[dev] = ok;
     return ok ? 0 : -1;
 }
@@ -963,7 +1047,7 @@ int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, con
                      const MOp *d_ops, const MBase *d_bases, const amp *mat_table, int sm_count,
                      const TileKnobs &knobs) {
     if (hdr.T < TILE_MIN_BITS || hdr.T > TILE_MAX_BITS || hdr.L > hdr.T || hdr.T - hdr.L > TILE_MAX_HIGH ||
-        hdr.n_tiles == 0 || hdr.n_ops == 0 || hdr.n_ops > (uint32_t)TILE_MAX_OPS ||
+        hdr.n_tiles == 0 || (hdr.n_ops == 0 && !hdr.remap) || hdr.n_ops > (uint32_t)TILE_MAX_OPS || hdr.n_stages == 0 ||
         hdr.n_stages > (uint32_t)TILE_MAX_STAGES)
         return -1;
     int threads;
@@ -974,8 +1058,12 @@ int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, con
         if (threads < 32) threads = 32;
         if (threads > 128) threads = 128;
     }
-    const tile_kernel_t kern = select_kernel(threads == 256 ? 256 : 128, knobs.ctas_per_sm, hdr.full != 0, knobs.bulk != 0);
-    const size_t smem = tile_smem_bytes(hdr, threads);
+    // two buffers only where three CTAs of 128 threads still fit the SM (long pass programs do not)
+    bool db = knobs.double_buffer != 0 && threads == 128 && hdr.T == 11 && !hdr.full && !knobs.bulk && knobs.ptx_ops &&
+              3 * (tile_smem_bytes(hdr, threads, true) + 1024) <= TILE_SMEM_MAX;
+    const tile_kernel_t kern = select_kernel(threads == 256 ? 256 : 128, knobs.ctas_per_sm, hdr.full != 0, knobs.bulk != 0,
+                                             knobs.ptx_ops != 0, db);
+    const size_t smem = tile_smem_bytes(hdr, threads, db);
     if (smem > TILE_SMEM_MAX) return -1;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1)

@@ -23,6 +23,9 @@ class PlanOp:
     ra: int
     rb: int
     scale: float = 0.0      # h1: the butterfly factor (1/sqrt2; halves of a split h2: 1 and 0.5)
+    pa: int = 0             # the same masks as index bits at scheduling time (differ after a remap pass)
+    pb: int = 0
+    pctrl: int = 0
 
 
 @dataclass
@@ -61,6 +64,9 @@ class PlanPass:
     peer: int = 0
     full: int = 0
     fx_val: int = 0
+    remap: int = 0          # the pass leaves rank bit rg and local bit rb exchanged (planner.cu)
+    rg: int = 0
+    rb: int = 0
     gpos: List[int] = field(default_factory=list)
     fx_pos: List[int] = field(default_factory=list)
     stages: List[PlanStage] = field(default_factory=list)
@@ -75,13 +81,13 @@ def _ints(s: str) -> List[int]:
 
 
 def describe(q_num: int, circ, rank: int = 0, world: int = 1, peers: bool = False, fuse: bool = True,
-             tile_bits: int = 0, chunk_bits: int = 0) -> List[PlanPass]:
+             tile_bits: int = 0, chunk_bits: int = 0, remap: bool = True) -> List[PlanPass]:
     if isinstance(circ, SingleOp):
         circ = MultiOp([circ])
     arr, n = circ.to_c_array()
     need = c_size_t(0)
     lib = _ffi.lib()
-    args = (q_num, rank, world, int(peers), int(fuse), tile_bits, chunk_bits, arr, n)
+    args = (q_num, rank, world, (1 if remap else 3) if peers else 0, int(fuse), tile_bits, chunk_bits, arr, n)
     _ffi.check(lib.qvnt_plan_describe(*args, None, 0, byref(need)))
     buf = ctypes.create_string_buffer(need.value)
     _ffi.check(lib.qvnt_plan_describe(*args, buf, need.value, byref(need)))
@@ -96,7 +102,8 @@ def describe(q_num: int, circ, rank: int = 0, world: int = 1, peers: bool = Fals
             else:
                 passes.append(PlanPass(direct=False, T=int(kv["T"]), L=int(kv["L"]), n_tiles=int(kv["n_tiles"]),
                                        base_or=int(kv["base_or"]), peer=int(kv["peer"]), full=int(kv.get("full", 0)),
-                                       fx_val=int(kv["fx_val"]),
+                                       fx_val=int(kv["fx_val"]), remap=int(kv.get("remap", 0)),
+                                       rg=int(kv.get("rg", 0)), rb=int(kv.get("rb", 0)),
                                        gpos=_ints(kv["gpos"]), fx_pos=_ints(kv["fx_pos"])))
         elif tok[0] == "stage":
             passes[-1].stages.append(PlanStage(r_lpos=_ints(kv["r"]), t_lpos=_ints(kv["t"]),

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from ctypes import byref, c_double, c_uint32, c_uint64, c_void_p
 from typing import Callable, Iterable, List, Optional, Union
 
@@ -120,6 +121,7 @@ class QReg:
         self.q_num = q_num
         self.q_mask = ((1 << q_num) - 1) & U64
         self.rank, self.world = 0, 1
+        self.group = False          # True: one handle over several GPUs (QReg.multi / num_threads)
 
     # -- constructors -------------------------------------------------------
     @classmethod
@@ -150,10 +152,34 @@ class QReg:
         buf = ctypes.create_string_buffer(raw, len(raw))
         _ffi.check(_ffi.lib().qvnt_reg_attach_peers(self._h, buf))
 
+    @classmethod
+    def multi(cls, q_num: int, state: int = 0, n_gpus: int = 1) -> "QReg":
+        """The register sharded by its top log2(n_gpus) qubits over n_gpus GPUs of this box, driven
+        from this one process through one handle (qvnt_reg_create_multi)."""
+        h = c_void_p()
+        _ffi.check(_ffi.lib().qvnt_reg_create_multi(q_num, state & U64, n_gpus, byref(h)))
+        r = cls(q_num, _handle=h)
+        r.world = max(1, n_gpus)
+        r.group = n_gpus > 1
+        return r
+
     def num_threads(self, num_threads: int) -> Optional["QReg"]:
-        """Source compatibility with quant.rs:186-200.  Parallelism is the GPU's;
-        the count is accepted (None for 0, like the reference) and ignored."""
-        return None if num_threads == 0 else self
+        """quant.rs:186-200 with GPUs for threads: the register continues on `num_threads` GPUs
+        (1, 2, 4 or 8 of this box: sharded by its top qubits, state kept).  Like the reference it
+        consumes `self` and answers None for 0 or for more than the box has."""
+        n = int(num_threads)
+        avail = 8 if os.environ.get("QVNT_MULTI_SHARE_DEVICES") else _ffi.device_count()
+        if n == 0 or n & (n - 1) or n > 8 or n > avail:
+            return None
+        if n == self.world and self.rank == 0:
+            return self
+        h = c_void_p()
+        _ffi.check(_ffi.lib().qvnt_reg_set_gpus(self._h, n, byref(h)))
+        r = QReg(self.q_num, _handle=h)
+        r.world = n
+        r.group = n > 1
+        self.close()
+        return r
 
     def clone(self) -> "QReg":
         h = c_void_p()
@@ -230,6 +256,8 @@ class QReg:
         return out.value
 
     def _local_range(self):
+        if self.group:
+            return 0, 1 << self.q_num
         n_local = self.q_num - (self.world.bit_length() - 1)
         return self.rank << n_local, 1 << n_local
 
@@ -259,36 +287,37 @@ class QReg:
         data = np.ascontiguousarray(data, dtype=np.complex128)
         _ffi.check(_ffi.lib().qvnt_reg_write(self._h, lo if off is None else off, data.size, data.ctypes.data))
 
-    def sample_all(self, count: int, rng: Optional[np.random.Generator] = None) -> List[int]:
-        """quant.rs:513-594: Gaussian approximation of `count` shots (statistical,
-        not bit, parity: the reference draws from thread_rng)."""
-        rng = rng or np.random.default_rng()
-        p = self.get_probabilities()
-        c = float(count)
-        n = np.sqrt(p) * rng.standard_normal(p.size)
-        n_sum = n.sum()
-        cnt = np.maximum(np.round(c * p + math.sqrt(c) * (n - n_sum * p)).astype(np.int64), 0)
-        delta = int(cnt.sum()) - count
-        if delta < 0:
-            d = -delta
-            q, rem = d >> self.q_num, d % self.q_mask if self.q_mask else 0
-            cnt += q
-            cnt[:rem] += 1
-        elif delta > 0:
-            idx = 0
-            while delta:
-                k = idx & self.q_mask
-                if cnt[k]:
-                    cnt[k] -= 1
-                    delta -= 1
-                idx += 1
-        return [int(v) for v in cnt]
+    def sample_all(self, count: int, seed: Optional[int] = None) -> np.ndarray:
+        """quant.rs:513-594: the histogram of `count` shots in the reference's Gaussian approximation
+        (no collapse), computed on the device (qvnt_reg_sample_all); statistical, not bit, parity --
+        the reference draws its normals from thread_rng."""
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little")
+        out = np.empty(1 << self.q_num, dtype=np.uint64)
+        _ffi.check(_ffi.lib().qvnt_reg_sample_all(self._h, int(count), seed & U64, out.ctypes.data))
+        return out
 
-    def get_vreg(self) -> VReg:                                   # quant.rs:232
-        return VReg.new_with_mask(self.q_mask)
+    # -- crate-private helpers of the reference (quant.rs:245-328) --------------------------------
+    @staticmethod
+    def combine(a: "QReg", b: "QReg") -> Optional["QReg"]:
+        if a.q_num != b.q_num:
+            return None
+        h = c_void_p()
+        _ffi.check(_ffi.lib().qvnt_reg_combine(a._h, b._h, byref(h)))
+        return QReg(a.q_num + 1, _handle=h)
 
-    def get_vreg_by(self, mask: int) -> Optional[VReg]:           # quant.rs:236
-        return None if mask & ~self.q_mask else VReg.new_with_mask(mask)
+    @staticmethod
+    def combine_with_unitary(a: "QReg", b: "QReg", c) -> Optional["QReg"]:
+        if a.q_num != b.q_num:
+            return None
+        m = np.ascontiguousarray(np.asarray(c, dtype=np.complex128).reshape(4))
+        h = c_void_p()
+        _ffi.check(_ffi.lib().qvnt_reg_combine_unitary(a._h, b._h, m.ctypes.data, byref(h)))
+        return QReg(a.q_num + 1, _handle=h)
+
+    def linear_composition(self, other: "QReg", c) -> None:
+        c0, c1 = complex(c[0]), complex(c[1])
+        _ffi.check(_ffi.lib().qvnt_reg_linear_composition(self._h, other._h, c0.real, c0.imag, c1.real, c1.imag))
 
     def __mul__(self, other: "QReg") -> "QReg":                   # tensor_prod quant.rs:330
         h = c_void_p()

@@ -69,6 +69,12 @@ extern "C" {
     pub fn qvnt_last_error() -> *const c_char;
     pub fn qvnt_device_count(out: *mut i32) -> i32;
     pub fn qvnt_reg_create(q_num: u32, state: u64, out: *mut *mut qvnt_reg_t) -> i32;
+    pub fn qvnt_reg_combine(a: *mut qvnt_reg_t, b: *mut qvnt_reg_t, out: *mut *mut qvnt_reg_t) -> i32;
+    pub fn qvnt_reg_combine_unitary(a: *mut qvnt_reg_t, b: *mut qvnt_reg_t, matrix8: *const f64, out: *mut *mut qvnt_reg_t) -> i32;
+    pub fn qvnt_reg_linear_composition(reg: *mut qvnt_reg_t, other: *mut qvnt_reg_t, c0_re: f64, c0_im: f64, c1_re: f64, c1_im: f64) -> i32;
+    pub fn qvnt_reg_sample_all(reg: *mut qvnt_reg_t, count: u64, seed: u64, host_out: *mut u64) -> i32;
+    pub fn qvnt_reg_create_multi(q_num: u32, state: u64, n_gpus: u32, out: *mut *mut qvnt_reg_t) -> i32;
+    pub fn qvnt_reg_set_gpus(reg: *mut qvnt_reg_t, n_gpus: u32, out: *mut *mut qvnt_reg_t) -> i32;
     pub fn qvnt_reg_create_sharded(q_num: u32, state: u64, rank: u32, world: u32, device: i32, out: *mut *mut qvnt_reg_t) -> i32;
     pub fn qvnt_reg_export_ipc(reg: *mut qvnt_reg_t, blob: *mut c_void) -> i32;
     pub fn qvnt_reg_attach_peers(reg: *mut qvnt_reg_t, blobs: *const c_void) -> i32;

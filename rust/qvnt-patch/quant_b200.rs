@@ -37,9 +37,18 @@ impl Reg {
         check(unsafe { sys::qvnt_reg_create(q_num as u32, state as u64, &mut dev) });
         Self { dev, q_num, q_mask: (1usize << q_num).wrapping_sub(1) }
     }
-    /// :186-200 -- parallelism is the GPU's; the shape `Option<Self>` is kept
-    pub fn num_threads(self, num_threads: usize) -> Option<Self> {
-        if num_threads == 0 { None } else { Some(self) }
+    /// :186-200 with GPUs for threads: the register continues on `num_threads` GPUs (1, 2, 4 or 8 of
+    /// this box, sharded by its top qubits, state kept); `None` for 0 or more than the box has
+    pub fn num_threads(mut self, num_threads: usize) -> Option<Self> {
+        let mut ndev = 0i32;
+        unsafe { sys::qvnt_device_count(&mut ndev) };
+        let n = num_threads;
+        if n == 0 || n & (n - 1) != 0 || n > 8 || n > ndev as usize { return None; }
+        let mut dev = null_mut();
+        check(unsafe { sys::qvnt_reg_set_gpus(self.dev, n as u32, &mut dev) });
+        unsafe { sys::qvnt_reg_destroy(self.dev) };
+        self.dev = dev;          // (Drop destroys the new handle)
+        Some(self)
     }
     pub fn num(&self) -> N { self.q_num }
     pub fn reset(&mut self, i_state: N) { check(unsafe { sys::qvnt_reg_reset(self.dev, i_state as u64) }) }

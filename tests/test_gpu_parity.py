@@ -310,7 +310,70 @@ def test_polar_clone_and_sample_all(oracle):
     c = g.clone()
     g.apply(op.x(1))                                  # the clone owns its own buffer
     assert np.abs(c.amplitudes() - a).max() <= AMP_TOL
-    hist = c.sample_all(2048, rng=np.random.default_rng(1))
-    assert len(hist) == 1 << n and sum(hist) == 2048
+    hist = c.sample_all(2048, seed=1)
+    assert len(hist) == 1 << n and int(hist.sum()) == 2048
     p = c.get_probabilities()
     assert np.abs(np.array(hist) / 2048.0 - p).max() < 0.05
+
+
+def test_sample_all_on_device_statistics(oracle):
+    """quant.rs:513-594 on the device: the histogram sums to `count` (the reference's +-delta
+    correction), is reproducible per seed, and every bin stays within the Gaussian model's spread
+    (mean c p_i, sigma sqrt(c p_i (1 - p_i))) -- statistical parity, the reference draws from
+    thread_rng.  Also over a one-handle multi-GPU register."""
+    import os
+    n = 14
+    circ = workloads.random_layered(n, 3)
+    g = QReg.new(n)
+    g.apply(circ)
+    p = g.get_probabilities()
+    mean, sd = oracle.sample_all_moments(p, 1 << 22)
+    for count in (1 << 22, 1000, 3):
+        h1 = g.sample_all(count, seed=7)
+        h2 = g.sample_all(count, seed=7)
+        h3 = g.sample_all(count, seed=8)
+        assert h1.dtype == np.uint64 and h1.size == 1 << n
+        assert int(h1.sum()) == count and int(h3.sum()) == count
+        assert np.array_equal(h1, h2)
+        if count > 1000:
+            assert not np.array_equal(h1, h3)
+            big = mean > 20.0                                 # bins where rounding to integers does not dominate
+            assert big.sum() > 100
+            z = (h1.astype(np.float64)[big] - mean[big]) / sd[big]
+            assert np.abs(z).max() < 7.0                      # |z| > 7 has probability ~ 1e-12 per bin
+            assert 0.8 < z.std() < 1.2                        # the spread is the model's, not zero
+            assert np.abs(h1.astype(np.float64)[~big] - mean[~big]).max() < 7.0 * np.sqrt(20.0) + 1.0
+    os.environ["QVNT_MULTI_SHARE_DEVICES"] = "1"
+    try:
+        m = QReg.multi(n, 0, 2)
+        m.apply(circ)
+        hm = m.sample_all(1 << 22, seed=7)
+        m.close()
+    finally:
+        del os.environ["QVNT_MULTI_SHARE_DEVICES"]
+    assert np.array_equal(hm, g.sample_all(1 << 22, seed=7))   # the generator is keyed by the global index
+    g.close()
+
+
+def test_combine_and_linear_composition(oracle):
+    """The crate-private register helpers of quant.rs:245-328 (untested in the reference) against
+    their numpy restatement."""
+    n = 9
+    a, oa = both(oracle, n, seed=3)
+    b, ob = both(oracle, n, seed=4)
+    va, vb = oa.amplitudes().copy(), ob.amplitudes().copy()
+    c = QReg.combine(a, b)
+    assert c.q_num == n + 1
+    assert np.array_equal(c.amplitudes(), oracle.combine(va, vb))
+    h = 0.5 ** 0.5
+    u = [h, h, h, -h]
+    cu = QReg.combine_with_unitary(a, b, u)
+    assert np.abs(cu.amplitudes() - oracle.combine_with_unitary(va, vb, u)).max() <= 1e-15
+    u2 = [0.6, 0.8j, 0.8j, 0.6]
+    cu2 = QReg.combine_with_unitary(a, b, u2)
+    assert np.abs(cu2.amplitudes() - oracle.combine_with_unitary(va, vb, u2)).max() <= 1e-15
+    assert QReg.combine(a, QReg.new(n + 1)) is None
+    a.linear_composition(b, (0.3 - 0.4j, 0.2 + 0.9j))
+    assert np.abs(a.amplitudes() - oracle.linear_composition(va, vb, (0.3 - 0.4j, 0.2 + 0.9j))).max() <= 1e-15
+    for r in (a, b, c, cu, cu2):
+        r.close()

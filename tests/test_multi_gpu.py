@@ -167,3 +167,73 @@ def test_sharded_lazy_x_large_tiles_regression():
     got, _, _ = run_sharded(n, 2, 0, circ)
     assert abs(float(np.vdot(got, got).real) - 1.0) < 1e-12
     assert np.abs(got - want).max() <= AMP_TOL
+
+
+# ---- one handle, one process, several GPUs (qvnt_reg_create_multi / QReg::num_threads) -------------
+@pytest.fixture
+def share_devices(monkeypatch):
+    """On a box with fewer GPUs than shards the shards share devices (test facility of the library)."""
+    monkeypatch.setenv("QVNT_MULTI_SHARE_DEVICES", "1")
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_one_handle_multi_gpu(oracle, share_devices, world):
+    n = 16
+    circ = workloads.random_layered(n, 6) * global_heavy(n, world) * op.qft((1 << n) - 1)
+    mask = (1 << (n - 1)) | 0b1011
+    reg = QReg.multi(n, 0x4321, world)
+    reg.apply(circ)
+    got = reg.amplitudes()
+    assert got.size == 1 << n
+    m = reg.measure_mask_full(mask, 0.4321)
+    got2 = reg.amplitudes()
+    p = reg.get_probabilities()
+    st = reg.stats()
+    reg.close()
+    want, mo, want2 = oracle_run(oracle, n, 0x4321, circ, measure=(mask, 0.4321))
+    assert np.abs(got - want).max() <= AMP_TOL
+    assert tuple(m) == tuple(mo)
+    assert np.abs(got2 - want2).max() <= AMP_TOL
+    assert abs(p.sum() - 1.0) < 1e-12
+    assert st["peer_bytes"] > 0
+
+
+def test_num_threads_moves_the_register_to_more_gpus(oracle, share_devices):
+    """QReg::num_threads (quant.rs:186-200) with GPUs for threads: the state survives the move."""
+    n = 15
+    c1 = workloads.random_layered(n, 3)
+    c2 = workloads.mixed_all_kinds(n, 40, seed=3) * op.h(1 << (n - 1))
+    reg = QReg.with_state(n, 5)
+    reg.apply(c1)
+    reg = reg.num_threads(4)
+    assert reg is not None and reg.world == 4
+    reg.apply(c2)
+    reg = reg.num_threads(1)
+    assert reg is not None and reg.world == 1
+    got = reg.amplitudes()
+    reg.close()
+    assert QReg.new(4).num_threads(0) is None
+    want, _, _ = oracle_run(oracle, n, 5, c1 * c2)
+    assert np.abs(got - want).max() <= AMP_TOL
+
+
+def test_remap_keeps_api_in_qubit_order(oracle, share_devices):
+    """After remap passes the qubits sit at other index bits; every index-addressed call
+    (read, probabilities, collapse, reset_by_mask, measure) must still see qubit order."""
+    n = 14
+    circ = workloads.random_layered(n, 5)
+    for world in (2, 4):
+        reg = QReg.multi(n, 0, world)
+        o = oracle.OracleReg.new(n, threads=oracle.max_threads())
+        reg.apply(circ)
+        o.apply(circ)
+        reg.collapse_mask(0b101 << (n - 3), 0b111 << (n - 3))
+        o.collapse_mask(0b101 << (n - 3), 0b111 << (n - 3))
+        reg.apply(circ)                     # a second apply continues from the restored layout
+        o.apply(circ)
+        reg.reset_by_mask(1 << (n - 1))
+        o.reset_by_mask(1 << (n - 1))
+        assert np.abs(reg.amplitudes() - o.amplitudes()).max() <= AMP_TOL
+        assert np.abs(reg.get_probabilities() - o.get_probabilities()).max() <= 1e-12
+        reg.close()
+        o.close()

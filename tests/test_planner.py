@@ -12,6 +12,14 @@ DIAG_KINDS = {op.K_Z, op.K_S, op.K_T, op.K_RZ, op.K_RZZ}
 QUAD_KINDS = {op.K_H2, op.K_U2}
 
 
+def _pmix(o):
+    """mix bits as index bits at scheduling time"""
+    import copy
+    q = copy.copy(o)
+    q.a, q.b = o.pa, o.pb
+    return _mix(q)
+
+
 def _mix(o):
     if o.kind in DIAG_KINDS:
         return 0
@@ -23,7 +31,7 @@ def check_structure(passes, q_num, world=1, rank=0):
     n_local = q_num - wb
     for p in passes:
         if p.direct:
-            assert _mix(p.op) >> n_local == 0          # global-qubit gates never run as direct sweeps
+            assert _pmix(p.op) >> n_local == 0         # global-qubit gates never run as direct sweeps
             continue
         assert 4 <= p.T <= 12 and p.L <= p.T and p.T - p.L <= 8
         assert p.gpos == sorted(set(p.gpos)) and len(p.gpos) == p.T
@@ -38,20 +46,20 @@ def check_structure(passes, q_num, world=1, rank=0):
             assert sorted(bits) == list(range(p.T))                  # a permutation of the tile-local bits
             regs = [p.gpos[l] for l in st.r_lpos]
             for o in st.ops:
-                m = _mix(o) if o.form != 5 else 0
+                m = _pmix(o) if o.form != 5 else 0
                 assert m & ~sum(1 << g for g in regs) == 0, "partner bit outside the register bits"
                 if o.form == 5:                                    # lazy x: a permutation between threads
-                    assert o.kind == op.K_X and o.a & tile_mask == o.a
-                    assert (o.a | o.ctrl) & sum(1 << g for g in regs) == 0
+                    assert o.kind == op.K_X and o.pa & tile_mask == o.pa
+                    assert (o.pa | o.pctrl) & sum(1 << g for g in regs) == 0
                 elif o.form == 7:                                  # lazy x on a register slot: slot marked inverted
-                    assert o.kind == op.K_X and 1 << regs[o.ra] == o.a
-                    assert o.ctrl & sum(1 << g for g in regs) == 0
+                    assert o.kind == op.K_X and 1 << regs[o.ra] == o.pa
+                    assert o.pctrl & sum(1 << g for g in regs) == 0
                 elif o.form == 1:
-                    assert 1 << regs[o.ra] == o.a
+                    assert 1 << regs[o.ra] == o.pa
                 elif o.form in (2, 3):
-                    assert (1 << regs[o.ra]) | (1 << regs[o.rb]) == o.a and regs[o.ra] < regs[o.rb]
+                    assert (1 << regs[o.ra]) | (1 << regs[o.rb]) == o.pa and regs[o.ra] < regs[o.rb]
                 elif o.form == 4:
-                    assert 1 << regs[o.ra] == o.a and 1 << regs[o.rb] == o.b
+                    assert 1 << regs[o.ra] == o.pa and 1 << regs[o.rb] == o.pb
                 else:
                     assert o.form == 0 and o.kind in DIAG_KINDS
 

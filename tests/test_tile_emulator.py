@@ -21,22 +21,35 @@ def _oracle_apply(oracle, n, psi, mop):
 
 
 def _emulate(oracle, n, circ, psi, world=1, **kw):
+    """psi is kept indexed by PHYSICAL index bits; `perm` (qubit -> index bit) follows the remap
+    passes; the result is returned indexed by qubits."""
     plans = [plan.describe(n, circ, rank=r, world=world, peers=world > 1, **kw) for r in range(world)]
-    n_fast = n_lazy = n_runs = 0
+    n_local = n - (world.bit_length() - 1)
+    perm = list(range(n))
+    n_fast = n_lazy = n_runs = n_remap = 0
     for k, p0 in enumerate(plans[0]):
         if p0.direct or p0.full:
             # direct sweeps and full-interpreter passes: their ops, in scheduled order, via the oracle
-            psi = _oracle_apply(oracle, n, psi, planned_sequence([p0], circ))
+            assert not (not p0.direct and p0.remap), "full-interpreter remap passes are covered on the GPU"
+            lg = _oracle_apply(oracle, n, emu.to_logical(psi, perm), planned_sequence([p0], circ))
+            psi = emu.to_physical(lg, perm)
             continue
         n_fast += 1
+        snap = psi.copy() if p0.remap else None
         for r in range(world):
             p = plans[r][k]
             assert not p.direct and not p.full and p.gpos == p0.gpos
-            emu.run_tile_pass(psi, p)
+            assert (p.remap, p.rg, p.rb) == (p0.remap, p0.rg, p0.rb)
+            emu.run_tile_pass(psi, p, rank=r, n_local=n_local, src=snap)
+        if p0.remap:
+            n_remap += 1
+            qa, qb = perm.index(p0.rg), perm.index(p0.rb)
+            perm[qa], perm[qb] = p0.rb, p0.rg
         for st in p0.stages:
-            n_lazy += sum(1 for m in st.mops if m.code in (emu.FC_LX, emu.FC_LI))
-            n_runs += sum(1 for m in st.mops if m.code in (emu.FC_DM, emu.FC_DM + emu.FC_MASKED))
-    return psi, n_fast, n_lazy, n_runs
+            n_lazy += sum(1 for m in st.mops if m.code % emu.FC_TOTAL in (emu.FC_LX, emu.FC_LI))
+            n_runs += sum(1 for m in st.mops if m.code % emu.FC_TOTAL in (emu.FC_DM, emu.FC_DM + emu.FC_MASKED))
+    _emulate.last_remaps = n_remap
+    return emu.to_logical(psi, perm), n_fast, n_lazy, n_runs
 
 
 def _state(n, seed):
@@ -104,5 +117,8 @@ def test_encoded_sharded_plan_reproduces_oracle(oracle, world):
     v = _state(n, 11 + world)
     want = _oracle_apply(oracle, n, v, circ)
     got, n_fast, _, _ = _emulate(oracle, n, circ, v.copy(), world=world)
-    assert n_fast >= 2
+    assert n_fast >= 2 and _emulate.last_remaps >= 2          # global qubits are swapped in, not exchanged twice
+    assert np.abs(got - want).max() <= 1e-12
+    got, _, _, _ = _emulate(oracle, n, circ, v.copy(), world=world, remap=False)
+    assert _emulate.last_remaps == 0
     assert np.abs(got - want).max() <= 1e-12

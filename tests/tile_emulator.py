@@ -16,7 +16,8 @@ from __future__ import annotations
 import numpy as np
 
 FC_PR, FC_PX, FC_DS, FC_DU, FC_DG, FC_LX, FC_LI, FC_DM, FC_MASKED, FC_SW = 0, 4, 8, 12, 13, 14, 15, 16, 17, 34
-MOP_SKIP0, MOP_COND, MOP_PARB, MOP_CONDB = 0x02, 0x04, 0x08, 0x10
+FC_TOTAL = 38
+MOP_SKIP0, MOP_COND, MOP_PARB, MOP_CONDB, MOP_ATHR = 0x02, 0x04, 0x08, 0x10, 0x20
 NV = 16
 U64 = (1 << 64) - 1
 
@@ -68,6 +69,8 @@ def run_stage(tile: np.ndarray, st, T: int, gbase: int):
     def dpar(m):
         if m.a_base:
             assert m.flags & MOP_PARB, "diagonal op with target bits outside the tile must carry MOP_PARB"
+        if m.a_thr:
+            assert m.flags & MOP_ATHR, "diagonal op with target bits on thread bits must carry MOP_ATHR"
         c = _popc(vgrp & m.a_thr)
         if m.flags & MOP_PARB:
             c = c + (_pc(gbase & m.a_base) & 7)
@@ -83,7 +86,8 @@ def run_stage(tile: np.ndarray, st, T: int, gbase: int):
 
     while i < len(mops):
         m = mops[i]
-        code = m.code
+        code = m.code % FC_TOTAL                 # the byte also carries the control class (engine.h)
+        assert m.code // FC_TOTAL == (2 if m.flags & MOP_CONDB else 1 if m.flags & MOP_COND else 0)
         masked = False
         if FC_MASKED <= code < FC_SW:
             code -= FC_MASKED
@@ -97,7 +101,7 @@ def run_stage(tile: np.ndarray, st, T: int, gbase: int):
             acc = np.ones(G, dtype=np.complex128)
             for k in range(1, cnt + 1):
                 e = mops[i + k]
-                assert e.code in (FC_DU, FC_MASKED + FC_DU) and e.okmask == m.okmask and e.ctrl_thr == m.ctrl_thr \
+                assert e.code % FC_TOTAL in (FC_DU, FC_MASKED + FC_DU) and e.okmask == m.okmask and e.ctrl_thr == m.ctrl_thr \
                     and e.ctrl_base == m.ctrl_base
                 par = dpar(e)
                 f = np.where(par == 1, complex(e.c[2], e.c[3]), complex(e.c[0], e.c[1]))
@@ -192,20 +196,52 @@ def run_stage(tile: np.ndarray, st, T: int, gbase: int):
     tile[dst] = regs
 
 
-def run_tile_pass(psi: np.ndarray, p):
-    """All tiles of one rank's pass `p` (plan.PlanPass, fast interpreter) on the GLOBAL state."""
+def run_tile_pass(psi: np.ndarray, p, rank: int = 0, n_local: int = 64, src: np.ndarray = None):
+    """All tiles of one rank's pass `p` (plan.PlanPass, fast interpreter) on the GLOBAL state (indexed
+    by PHYSICAL index bits).  Tiles are read from `src` (default: psi itself) and written to psi.
+    A remap pass (p.remap) writes both halves of every tile into the rank's own shard, the value of
+    the rank bit rg going to local bit rb -- the caller must then read every rank's tiles from a
+    snapshot taken before the pass (on the GPU a per-tile handshake orders the two)."""
     T = p.T
+    src = psi if src is None else src
     jj = np.arange(1 << T, dtype=np.int64)
     scat = np.zeros(1 << T, dtype=np.int64)
+    scat_st = np.zeros(1 << T, dtype=np.int64)
     for l, g in enumerate(p.gpos):
         scat |= ((jj >> l) & 1) << g
+        scat_st |= ((jj >> l) & 1) << (p.rb if (p.remap and g == p.rg) else g)
     for t in range(p.n_tiles):
         base = t
         for pos in p.fx_pos:
             base = ((base >> pos) << (pos + 1)) | (base & ((1 << pos) - 1))
         gbase = base | p.fx_val | p.base_or
         idx = gbase | scat
-        tile = psi[idx].copy()
+        tile = src[idx].copy()
         for st in p.stages:
             run_stage(tile, st, T, gbase)
-        psi[idx] = tile
+        if p.remap:
+            sbase = ((base | p.fx_val) & ~(1 << p.rb)) | (rank << n_local)
+            psi[sbase | scat_st] = tile
+        else:
+            psi[idx] = tile
+
+
+def to_logical(psi: np.ndarray, perm) -> np.ndarray:
+    """State indexed by index bits (qubit q at bit perm[q]) -> indexed by qubits."""
+    n = len(perm)
+    x = np.arange(1 << n, dtype=np.int64)
+    y = np.zeros(1 << n, dtype=np.int64)
+    for q in range(n):
+        y |= ((x >> q) & 1) << perm[q]
+    return psi[y]
+
+
+def to_physical(psi_l: np.ndarray, perm) -> np.ndarray:
+    n = len(perm)
+    x = np.arange(1 << n, dtype=np.int64)
+    y = np.zeros(1 << n, dtype=np.int64)
+    for q in range(n):
+        y |= ((x >> q) & 1) << perm[q]
+    out = np.empty_like(psi_l)
+    out[y] = psi_l
+    return out

@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/r02c_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02c_pytest.log
+tail -6 gpurun_out/r02c_pytest.log
 out=gpurun_out/r02c_sweep.txt; : > $out
 run() { echo "== $*" >> $out; timeout 300 python bench.py --qubits 30 --steps 2 --warmup 1 --no-cpu --no-check "$@" 2>>gpurun_out/r02c_err.txt | python -c "
 import sys,json
@@ -8,11 +10,14 @@ for l in sys.stdin:
     except Exception: continue
     r=d['roofline']; print(f\"{d['value']:.0f} gates/s {d['ms_per_step']:.0f} ms/step {r['avg_launch_ms']:.3f} ms/pass frac {r['frac']:.3f} passes {r['passes_per_step']} e2e {d['e2e']['value']:.0f}\")
 " >> $out; }
-run --tma 1 --opt prefetch=1
-run --tma 1 --opt prefetch=0
-run --tma 0 --opt prefetch=1
-run --tma 0 --opt prefetch=0
-run --tma 0 --opt prefetch=1 --chunk-bits 3
-run --tma 0 --opt prefetch=1 --tile-bits 10 --chunk-bits 3
-run --tma 0 --opt prefetch=1 --tile-bits 12
+run --tma 1 --opt prefetch=1 ptx_ops=1
+run --tma 1 --opt prefetch=0 ptx_ops=1
+run --tma 0 --opt prefetch=1 ptx_ops=1
+run --tma 0 --opt prefetch=0 ptx_ops=1
+run --tma 0 --opt prefetch=0 ptx_ops=0
+run --tma 0 --opt prefetch=1 ptx_ops=1 --chunk-bits 3
+run --tma 0 --opt prefetch=1 ptx_ops=1 --tile-bits 10 --chunk-bits 3
+run --tma 0 --opt prefetch=1 ptx_ops=1 --tile-bits 12
+run --tma 0 --opt prefetch=1 ptx_ops=1 tile_ctas=3
 cat $out
+timeout 300 python tools/tile_probe.py --qubits 30 --tile-bits 11 --chunk-bits 4 --tma 0 > gpurun_out/r02c_probe.txt 2>&1; cat gpurun_out/r02c_probe.txt

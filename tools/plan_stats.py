@@ -47,7 +47,8 @@ def main():
                     cnt["diag_run_member"] += 1
                     skip -= 1
                     continue
-                c = m.code - 17 if 17 <= m.code < 34 else m.code
+                c = m.code % 38
+                c = c - 17 if 17 <= c < 34 else c
                 base = max(k for k in NAMES if k <= c)
                 cnt[NAMES[base]] += 1
                 if base == 16:
