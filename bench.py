@@ -335,7 +335,7 @@ def run_ours(args):
         reg.set_option("fuse", 0)
     if args.ctas:
         reg.set_option("tile_ctas", args.ctas)
-    if args.tma >= 0:
+    if args.tma >= -1:
         reg.set_option("tma", args.tma)
     for kv in args.opt:
         k, v = kv.split("=")
@@ -458,7 +458,8 @@ def run_ours(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": cfg,
         "engine": {"fuse": not args.no_fuse, "tile_bits": args.tile_bits or 11, "chunk_bits": args.chunk_bits or 4,
-                   "tile_loads": "cp.async.bulk + mbarrier" if args.tma == 1 else "cp.async 16 B, two tile buffers"},
+                   "tile_loads": ("cp.async.bulk + mbarrier" if args.tma == 1 else "cp.async 16 B" if args.tma == 0 else
+                                  "cp.async 16 B (local passes), cp.async.bulk + mbarrier (passes that read a peer shard)")},
         "equivalent_unfused_gbs": value * 32 * (1 << n) / 1e9,
         "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
         "parity_check": parity,
@@ -497,7 +498,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=150.0, help="reference arm: budget for all timed sweeps")
     ap.add_argument("--tile-bits", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0, help="CTAs per SM of the tile pass for T <= 11 (0 = auto, 3..5)")
-    ap.add_argument("--tma", type=int, default=-1, help="1: cp.async.bulk tile loads (default), 0: 16-byte cp.async")
+    ap.add_argument("--tma", type=int, default=-2, help="tile loads: 1 cp.async.bulk, 0 16-byte cp.async, -1/default auto (bulk for peer passes)")
     ap.add_argument("--chunk-bits", type=int, default=0)
     ap.add_argument("--opt", nargs="*", default=[], help="library options key=value")
     ap.add_argument("--no-fuse", action="store_true", help="one in-place sweep per SingleOp")

@@ -177,9 +177,13 @@ int qvnt_reg_sync(qvnt_reg_t *reg);
 /* ---- tuning / instrumentation --------------------------------------------- */
 /* keys: "fuse" (0/1); "tile_bits" (0 = auto, 6..12: amplitudes per tile of the fused pass);
  * "chunk_bits" (0 = auto, 2..12: contiguous amplitudes per chunk of a tile; at least two tile bits
- * are always left for gathered qubits); "tma" (1: tile loads by cp.async.bulk + mbarrier, default;
- * 0: 16-byte cp.async); "tile_ctas" (0 = auto, 3..5 CTAs per SM for 2^11-amplitude tiles);
- * "profile" (0/1: time every launch with CUDA events); "seed". */
+ * are always left for gathered qubits); "tma" (tile loads: 1 cp.async.bulk + mbarrier, 0 16-byte
+ * cp.async, -1 = auto, default: bulk copies for passes that read a peer shard); "tile_ctas" (0 =
+ * auto, 3..5 CTAs per SM for 2^11-amplitude tiles); "ptx_ops" (1, default: the fast interpreter's
+ * op loop as one inline-PTX block; 0: the C++ loop); "remap" (1, default: a pass on a global qubit
+ * leaves it local -- logical -> physical qubit map; 0: exchange and write back);
+ * "double_buffer", "prefetch" (experiments, off); "profile" (0/1: time every launch with CUDA
+ * events); "seed". */
 int qvnt_reg_set_option(qvnt_reg_t *reg, const char *key, int64_t value);
 int qvnt_reg_stats(qvnt_reg_t *reg, qvnt_stats_t *out);
 int qvnt_reg_stats_reset(qvnt_reg_t *reg);

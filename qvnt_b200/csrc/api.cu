@@ -1118,7 +1118,7 @@ int qvnt_reg_set_option(qvnt_reg_t *r, const char *key, int64_t value) {
             return QVNT_ERR_INVALID;
         }
         r->opt_chunk_bits = (int)value;
-    } else if (!strcmp(key, "tma")) r->knobs.bulk = value != 0;
+    } else if (!strcmp(key, "tma")) r->knobs.bulk = value < 0 ? -1 : value != 0;
     else if (!strcmp(key, "remap")) {
         int rc = use(r);
         if (rc) return rc;
@@ -1128,8 +1128,8 @@ int qvnt_reg_set_option(qvnt_reg_t *r, const char *key, int64_t value) {
     else if (!strcmp(key, "ptx_ops")) r->knobs.ptx_ops = value != 0;
     else if (!strcmp(key, "double_buffer")) r->knobs.double_buffer = value != 0;
     else if (!strcmp(key, "tile_ctas")) {
-        if (value != 0 && (value < 3 || value > 4)) {
-            set_error("tile_ctas must be 0 (auto), 3 or 4");
+        if (value != 0 && (value < 3 || value > 5)) {
+            set_error("tile_ctas must be 0 (auto) or 3..5");
             return QVNT_ERR_INVALID;
         }
         r->knobs.ctas_per_sm = (int)value;

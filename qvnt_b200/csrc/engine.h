@@ -124,6 +124,11 @@ constexpr uint8_t MOP_PARB = 0x08;    // flags bit 3 (diagonal forms): target bi
                                       //   the per-tile flag byte carries their parity
 constexpr uint8_t MOP_CONDB = 0x10;   // flags bit 4: ... and some of them outside the tile (ctrl_base != 0): read the flag byte
 constexpr uint8_t MOP_ATHR = 0x20;    // flags bit 5 (diagonal forms): target bits on thread bits (a_thr != 0)
+constexpr uint8_t MOP_STATIC = 0x40;  // flags bit 6 (FC_DM header): every member's target is either on thread bits or outside the
+                                      //   tile and no lazy x precedes the run in its stage: the per-thread factor of the thread-bit
+                                      //   members is tabulated once per kernel (slot = header's a_thr), the factor of the
+                                      //   outside members once per tile (MOP_PARB on the header: there are such members)
+constexpr int TILE_MAX_STATIC = 12;   // tabulated runs per pass (2 KiB of shared memory each at 128 threads)
 constexpr uint32_t MOP_ALT_BYTES = 32; // byte distance from the coefficient block to the `alt` block
 
 struct __align__(16) MOp {   // 80 bytes, staged in shared memory
@@ -180,7 +185,9 @@ struct TPassHdr {
     uint8_t gpos_store[16];      // tile-local bit -> bit position the last stage stores it to (== gpos unless remap)
     uint32_t full;               // some op needs the full interpreter (u1/u2, two-bit pair ops, multi-bit masks)
     uint32_t need_flags;         // some op of the pass depends on index bits outside the tile (per-tile flag bytes)
+    uint32_t n_static;           // tabulated diagonal runs (MOP_STATIC headers) of the pass
     uint32_t prefetch;           // filled by launch_tile_pass (TileKnobs): L2 prefetch of the next tile's chunks
+    uint32_t _pad4;
     uint64_t fixed_mask;         // local index bits the tile counter does NOT enumerate (tile bits + ownership bits)
     uint16_t stage_end[TILE_MAX_STAGES];   // ops of stage s: [stage_end[s-1], stage_end[s]) relative to op_begin
     Fixed fx;                    // the same enumeration bit by bit (host side: describe / tests)
@@ -189,10 +196,12 @@ struct TPassHdr {
 // Per-handle tuning knobs of the tile pass (qvnt_reg_set_option): no process-global state.
 struct TileKnobs {
     int ctas_per_sm = 0;   // 0 = auto (3 x 128 threads at 168 registers for 2^11 tiles: no spills; 2 x 256 for 2^12); 4: forced
-    int bulk = 0;          // 1: tile loads by cp.async.bulk (TMA) + mbarrier; 0: 16-byte cp.async (measured faster
-                           //    at 256-byte chunks: a bulk copy costs its issuing lane ~17 instructions)
+    int bulk = -1;         // tile loads: 1 = cp.async.bulk (TMA) + mbarrier, 0 = 16-byte cp.async, -1 = auto: bulk copies
+                           //    for passes that read a peer shard (fewer, larger NVLink requests: measured +7 % at
+                           //    2 GPUs), cp.async for local passes (a 256-byte bulk copy costs its issuing lane ~17
+                           //    instructions: measured -8 % on one GPU)
     int prefetch = 0;      // 1: cp.async.bulk.prefetch.L2 of tile i+1 while tile i computes (measured: no gain, off)
-    int double_buffer = 0; // 1: two tile buffers per CTA where three CTAs per SM still fit (2^11 tiles, cp.async loads)
+    int double_buffer = 0; // 1: two tile buffers per CTA (2^11 tiles, cp.async loads); measured no gain, local or peer: off
     int ptx_ops = 1;       // 1: the fast interpreter's op loop as one inline-PTX block (fastops_ptx.inc); 0: C++ loop
 };
 int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, const TStage *d_stages,

@@ -17,7 +17,9 @@ SOMETIMES needs is kept off that path:
 Operands of the asm statement (tile.cu, stage_ops_fast_ptx):
   %0..%31  the 16 register-resident amplitudes, v[K].x = %(2K), v[K].y = %(2K+1)      ("+d")
   %32 vgrp  %33 inv  %34 jl  %35 mine_o ("+r")   %36 goff ("+l")
-  %37 first op (shared-window address)  %38 end  %39 this tile's flag bytes ("r")
+  %37 first op (shared-window address)  %38 end  %39 this tile's flag bytes
+  %40 this thread's column of the tabulated-run table  %41 this tile's outside-the-tile factors
+  %42 byte stride between runs in the table ("r")
 
 Descriptor layout: engine.h MOp (80 bytes): w0 = code | flags << 8 | okmask << 16, ctrl_thr, a_thr,
 w3 = a_reg | idx << 16, c0..c3 at +16, alt block at +48.  Codes: engine.h FCode.
@@ -26,7 +28,7 @@ import sys
 
 NV = 16
 FC_PR, FC_PX, FC_DS, FC_DU, FC_DG, FC_LX, FC_LI, FC_DM, FC_MASKED, FC_SW, FC_TOTAL = 0, 4, 8, 12, 13, 14, 15, 16, 17, 34, 38
-SKIP0, COND, PARB, CONDB, ATHR = 0x02 << 8, 0x04 << 8, 0x08 << 8, 0x10 << 8, 0x20 << 8
+SKIP0, COND, PARB, CONDB, ATHR, STATIC = 0x02 << 8, 0x04 << 8, 0x08 << 8, 0x10 << 8, 0x20 << 8, 0x40 << 8
 MOP = 80
 
 L = []
@@ -379,6 +381,27 @@ def gen():
         e(f"${pre}DM:")
         reload()
         e("and.b32 cnt, w3, 65535;")
+        # tabulated run (MOP_STATIC): one load for the thread-bit members, one for the members outside the tile
+        e(f"and.b32 u, w0, {STATIC};")
+        e("setp.eq.u32 pk, u, 0;")
+        e(f"@pk bra.uni ${pre}DMd;")
+        e("mad.lo.u32 ca, w2, %42, %40;")
+        e("ld.shared.v2.f64 {ar, ai}, [ca];")
+        e(f"mad.lo.u32 p, cnt, {MOP}, p;")
+        e(f"and.b32 u, w0, {PARB};")
+        e("setp.eq.u32 pk, u, 0;")
+        e(f"@pk bra.uni ${pre}DMa;")
+        e("shl.b32 t, w2, 4;")
+        e("add.u32 ca, t, %41;")
+        e("ld.shared.v2.f64 {fr, fi}, [ca];")
+        e("mul.rn.f64 ta, ai, fi;")
+        e("mul.rn.f64 tb, ai, fr;")
+        e("neg.f64 ta, ta;")
+        e("fma.rn.f64 ta, ar, fr, ta;")
+        e("fma.rn.f64 ai, ar, fi, tb;")
+        e("mov.f64 ar, ta;")
+        e(f"bra.uni ${pre}DMa;")
+        e(f"${pre}DMd:")
         e("mov.f64 ar, 0d3FF0000000000000;")
         e("mov.f64 ai, 0d0000000000000000;")
         e(f"${pre}DMl:")

@@ -606,7 +606,10 @@ static int build_plan(const PlanCfg &c, std::vector<POp> &pl, Plan &plan) {
         cur.ops.clear();
         cur.hdr.stage_begin = (uint32_t)plan.stages.size();
         cur.hdr.op_begin = (uint32_t)plan.mops.size();
+        int cur_static = 0;
         auto flush = [&]() {
+            cur.hdr.n_static = (uint32_t)cur_static;
+            cur_static = 0;
             cur.hdr.n_stages = (uint32_t)plan.stages.size() - cur.hdr.stage_begin;
             cur.hdr.n_ops = (uint32_t)plan.mops.size() - cur.hdr.op_begin;
             for (uint32_t k = 0; k < cur.hdr.n_stages; ++k)
@@ -874,6 +877,8 @@ static int build_plan(const PlanCfg &c, std::vector<POp> &pl, Plan &plan) {
                 plan.mops.resize(b0);
                 plan.bases.resize(b0);
                 plan.minfo.resize(b0);
+                bool stage_has_lx = false;
+                for (const MOp &q : mo) stage_has_lx = stage_has_lx || q.code == (uint8_t)FC_LX;
                 auto is_du = [&](size_t k) {
                     return mo[k].code == (uint8_t)FC_DU || mo[k].code == (uint8_t)(FC_MASKED + FC_DU);
                 };
@@ -892,6 +897,19 @@ static int build_plan(const PlanCfg &c, std::vector<POp> &pl, Plan &plan) {
                         memset(&hb, 0, sizeof(hb));
                         hd.code = (uint8_t)(mo[k].okmask == 0xFFFFu ? FC_DM : FC_DM + FC_MASKED);
                         hd.dagger = (uint8_t)(mo[k].dagger & (MOP_COND | MOP_CONDB));
+                        // tabulated run (engine.h MOP_STATIC): targets on thread bits XOR outside the tile, and
+                        // the thread's group number still is its thread index (no lazy x in the stage)
+                        bool is_static = !stage_has_lx && cur_static < TILE_MAX_STATIC;
+                        bool outer = false;
+                        for (size_t q = k; q < e && is_static; ++q) {
+                            is_static = (mo[q].a_thr != 0) != (ba[q].a_base != 0);
+                            outer = outer || ba[q].a_base != 0;
+                        }
+                        if (is_static) {
+                            hd.dagger |= MOP_STATIC;
+                            if (outer) hd.dagger |= MOP_PARB;
+                            hd.a_thr = (uint32_t)cur_static++;
+                        }
                         hd.okmask = mo[k].okmask;
                         hd.ctrl_thr = mo[k].ctrl_thr;
                         hd.a_reg = (uint16_t)(e - k);

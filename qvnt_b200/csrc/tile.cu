@@ -579,7 +579,9 @@ __device__ __forceinline__ void farm_dg(amp (&v)[NV], const unsigned char *op, c
 // The op loop of the FAST interpreter.
 __device__ __forceinline__ void stage_ops_fast(const unsigned char *ops, const volatile uint8_t *flags, const uint32_t ob,
                                                const uint32_t oe, const uint32_t grp, const uint32_t L, StageCtx &x,
-                                               uint32_t &inv, amp (&v)[NV]) {
+                                               uint32_t &inv, amp (&v)[NV], const double2 *dtab, const uint32_t dstride,
+                                               const volatile double2 *dout_v) {
+    const double2 *dout = const_cast<const double2 *>(dout_v);
     uint32_t vgrp = grp;
     const unsigned char *p = ops + MOP_BYTES * ob;
     const unsigned char *const pe = ops + MOP_BYTES * oe;
@@ -627,6 +629,17 @@ __device__ __forceinline__ void stage_ops_fast(const unsigned char *ops, const v
             // merged diagonal run: acc = product of the constituents' factors for this thread
             const uint32_t cnt = h.w & 0xFFFFu;
             double ar = 1.0, ai = 0.0;
+            if (h.x & ((uint32_t)MOP_STATIC << 8)) {        // tabulated (engine.h MOP_STATIC)
+                const double2 a = dtab[h.z * dstride];
+                ar = a.x;
+                ai = a.y;
+                if (h.x & ((uint32_t)MOP_PARB << 8)) {
+                    const double2 f = dout[h.z];
+                    ar = a.x * f.x - a.y * f.y;
+                    ai = a.x * f.y + a.y * f.x;
+                }
+                p += MOP_BYTES * cnt;
+            } else
             for (uint32_t k = 0; k < cnt; ++k, p += MOP_BYTES) {
                 const uint4 h2 = *reinterpret_cast<const uint4 *>(p);
                 const uint32_t par = dpar(h2.x, h2.z, h2.w >> 16);
@@ -661,7 +674,8 @@ __device__ __forceinline__ void stage_ops_fast(const unsigned char *ops, const v
 // specification and the A/B baseline.
 __device__ __forceinline__ void stage_ops_fast_ptx(const uint32_t ops_s, const uint32_t flags_s, const uint32_t ob,
                                                    const uint32_t oe, const uint32_t grp, StageCtx &x, uint32_t &inv,
-                                                   amp (&v)[NV]) {
+                                                   amp (&v)[NV], const uint32_t dtab_s, const uint32_t dstride_bytes,
+                                                   const uint32_t dout_s) {
     uint32_t vgrp = grp;
     const uint32_t pb = ops_s + MOP_BYTES * ob, pe = ops_s + MOP_BYTES * oe;
     asm volatile(QV_FASTOPS_PTX
@@ -671,7 +685,7 @@ __device__ __forceinline__ void stage_ops_fast_ptx(const uint32_t ops_s, const u
                    "+d"(v[10].y), "+d"(v[11].x), "+d"(v[11].y), "+d"(v[12].x), "+d"(v[12].y), "+d"(v[13].x),
                    "+d"(v[13].y), "+d"(v[14].x), "+d"(v[14].y), "+d"(v[15].x), "+d"(v[15].y), "+r"(vgrp), "+r"(inv),
                    "+r"(x.jl), "+r"(x.mine_o), "+l"(x.goff)
-                 : "r"(pb), "r"(pe), "r"(flags_s)
+                 : "r"(pb), "r"(pe), "r"(flags_s), "r"(dtab_s), "r"(dout_s), "r"(dstride_bytes)
                  : "memory");
 }
 
@@ -711,7 +725,8 @@ __device__ __forceinline__ void bulk_prefetch_l2(const unsigned long long src, c
 // One buffer per CTA: the last stage stores its registers straight to HBM, so the buffer is free
 // as soon as that stage has read it -- the next tile's load is issued right there and overlaps
 // the last stage's arithmetic and stores.
-constexpr uint32_t META_SLOTS = 3;      // per-tile op flags rotate through 3 slots: preparing tile i+1 must not
+constexpr uint32_t META_SLOTS = 3;
+__host__ __device__ inline bool need_flags_smem(const TPassHdr &h, bool full) { return full || h.need_flags != 0u; }      // per-tile op flags rotate through 3 slots: preparing tile i+1 must not
                                         // race with the threads still running the ops of tile i-1
 
 template <int THREADS, int MINB, bool FULL, bool BULK, bool PTXOPS, bool DB>
@@ -743,6 +758,12 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     uint32_t *s_jltab = reinterpret_cast<uint32_t *>(s_ctab + n_stages);           // 4 * nthr * n_stages
     uint8_t *s_gpos = reinterpret_cast<uint8_t *>(s_jltab + nthr * n_stages);      // 16
     uint8_t *s_flags_all = s_gpos + 16;                                            // 3 * flags_stride (need_flags)
+    // tabulated diagonal runs (MOP_STATIC): [run][thread] factor of the thread-bit members (once per
+    // kernel) and [flag slot][run] factor of the members outside the tile (once per tile)
+    const uint32_t n_static = hdr.n_static;
+    const uint32_t flags_bytes = need_flags_smem(hdr, FULL) ? META_SLOTS * flags_stride : 16u;
+    double2 *s_dtab = reinterpret_cast<double2 *>(s_flags_all + flags_bytes);      // 16 * nthr * n_static
+    double2 *s_dout = s_dtab + (size_t)nthr * n_static;                            // 16 * META_SLOTS * n_static
 
     const uint32_t shard_shift = segs.shift;
     const uint64_t shard_mask = (1ull << shard_shift) - 1ull;
@@ -786,6 +807,27 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
             for (uint32_t l = 0; l < T; ++l)
                 if ((jl >> l) & 1u) go += 16ull << hdr.gpos_store[l];
             my_goff = go;
+        }
+    }
+    if (!FULL && n_static) {
+        // factor of every tabulated run's thread-bit members for THIS thread (its group number is its index)
+        for (uint32_t o = 0; o < n_ops; ++o) {
+            const MOp &hd = s_ops[o];
+            const uint32_t base_code = hd.code % (uint32_t)FC_TOTAL;
+            if ((base_code != (uint32_t)FC_DM && base_code != (uint32_t)(FC_DM + FC_MASKED)) || !(hd.dagger & MOP_STATIC)) continue;
+            double ar = 1.0, ai = 0.0;
+            for (uint32_t k = 1; k <= hd.a_reg; ++k) {
+                const MOp &m = s_ops[o + k];
+                if (!m.a_thr) continue;
+                const uint32_t par = (uint32_t)__popc(tid & m.a_thr) & 1u;
+                if (!par && (m.dagger & MOP_SKIP0)) continue;
+                const double fr = par ? m.c2 : m.ph_re, fi = par ? m.c3 : m.ph_im;
+                const double t = ar * fr - ai * fi;
+                ai = ar * fi + ai * fr;
+                ar = t;
+            }
+            s_dtab[hd.a_thr * nthr + tid] = make_double2(ar, ai);
+            o += hd.a_reg;
         }
     }
     const uint32_t tile_s0 = (uint32_t)__cvta_generic_to_shared(tile_b);
@@ -839,6 +881,27 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
                 const uint32_t okb = ((~gb & b.ctrl_base) == 0) ? 0x80u : 0u;
                 flags[o] = (uint8_t)(okb | ((uint32_t)__popcll(gb & b.a_base) & 7u));
                 any |= (int)okb;
+                if (!FULL && n_static) {
+                    const MOp &hd = s_ops[o];
+                    const uint32_t base_code = hd.code % (uint32_t)FC_TOTAL;
+                    if ((base_code == (uint32_t)FC_DM || base_code == (uint32_t)(FC_DM + FC_MASKED)) &&
+                        (hd.dagger & MOP_STATIC) && (hd.dagger & MOP_PARB)) {
+                        // this tile's factor of the run's members outside the tile
+                        double ar = 1.0, ai = 0.0;
+                        for (uint32_t k = 1; k <= hd.a_reg; ++k) {
+                            const uint64_t ab = s_bases[o + k].a_base;
+                            if (!ab) continue;
+                            const MOp &m = s_ops[o + k];
+                            const uint32_t par = (uint32_t)__popcll(gb & ab) & 1u;
+                            if (!par && (m.dagger & MOP_SKIP0)) continue;
+                            const double fr = par ? m.c2 : m.ph_re, fi = par ? m.c3 : m.ph_im;
+                            const double t = ar * fr - ai * fi;
+                            ai = ar * fi + ai * fr;
+                            ar = t;
+                        }
+                        s_dout[slot * n_static + hd.a_thr] = make_double2(ar, ai);
+                    }
+                }
             }
             if (remap) any = 1;                          // every tile moves
             if (__syncthreads_or(any)) return;
@@ -975,8 +1038,13 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
             if (active) {
                 uint32_t inv = 0;
                 if (FULL) stage_ops_full(ops_s, flags_s, ob, oe, tid, mats, v);
-                else if (PTXOPS) stage_ops_fast_ptx(ops_s, flags_s, ob, oe, tid, x, inv, v);
-                else stage_ops_fast(reinterpret_cast<const unsigned char *>(s_ops), flags, ob, oe, tid, L, x, inv, v);
+                else if (PTXOPS)
+                    stage_ops_fast_ptx(ops_s, flags_s, ob, oe, tid, x, inv, v,
+                                       (uint32_t)__cvta_generic_to_shared(s_dtab + tid), 16u * nthr,
+                                       (uint32_t)__cvta_generic_to_shared(s_dout + mslot * n_static));
+                else
+                    stage_ops_fast(reinterpret_cast<const unsigned char *>(s_ops), flags, ob, oe, tid, L, x, inv, v,
+                                   s_dtab + tid, nthr, s_dout + mslot * n_static);
                 if (!last) stage_store_smem(tile_s, x, inv, v);
                 else if (hdr.touches_peer && !remap) stage_store_global(ptr0_s, L, toff_cur, x, inv, v);
                 else stage_store_global_local(shard_base + (toff_cur & store_keep), s_gpos, x, inv, v);
@@ -1002,7 +1070,8 @@ static size_t tile_smem_bytes(const TPassHdr &h, int threads, bool db = false) {
     return (db ? 2 : 1) * (((size_t)16 << h.T) + ((size_t)16 << (h.T - h.L))) + 16 + (size_t)MOP_BYTES * h.n_ops +
            (flags ? sizeof(MBase) * h.n_ops : 0) + (size_t)32 * h.n_stages + (((size_t)8 << (h.T - h.L)) + 8) +
            (size_t)16 * h.n_stages + (size_t)4 * threads * h.n_stages + 16 +
-           (flags ? (size_t)META_SLOTS * ((h.n_ops + 15u) & ~15u) : 16);
+           (flags ? (size_t)META_SLOTS * ((h.n_ops + 15u) & ~15u) : 16) +
+           (size_t)16 * h.n_static * ((size_t)threads + META_SLOTS);
 }
 
 typedef void (*tile_kernel_t)(const Segs, const TPassHdr, const TStage *, const MOp *, const MBase *, const amp *);
@@ -1019,6 +1088,7 @@ static tile_kernel_t select_kernel(int threads, int ctas, bool full, bool bulk, 
     if (db && threads == 128 && !full && !bulk && ptx) return k_tile_pass<128, 3, false, false, true, true>;
     if (threads == 256) return pick_kernel<256, 2>(full, bulk, ptx);
     if (ctas == 4) return pick_kernel<128, 4>(full, bulk, ptx);
+    if (ctas == 5 && !full && !bulk && ptx) return k_tile_pass<128, 5, false, false, true, false>;
     return pick_kernel<128, 3>(full, bulk, ptx);
 }
 
@@ -1034,8 +1104,8 @@ int tile_kernel_setup() {
     for (int full = 0; full < 2; ++full)
         for (int bulk = 0; bulk < 2; ++bulk)
             for (int ptx = 0; ptx < 2; ++ptx)
-                for (int cfg = 0; cfg < 4; ++cfg) {
-                    const tile_kernel_t k = select_kernel(cfg == 0 ? 256 : 128, cfg == 1 ? 3 : 4, full, bulk, ptx, cfg == 3);
+                for (int cfg = 0; cfg < 5; ++cfg) {
+                    const tile_kernel_t k = select_kernel(cfg == 0 ? 256 : 128, cfg == 1 ? 3 : cfg == 4 ? 5 : 4, full, bulk, ptx, cfg == 3);
                     ok = ok && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                     (int)TILE_SMEM_MAX) == cudaSuccess;
                 }
@@ -1058,10 +1128,13 @@ int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, con
         if (threads < 32) threads = 32;
         if (threads > 128) threads = 128;
     }
-    // two buffers only where three CTAs of 128 threads still fit the SM (long pass programs do not)
-    bool db = knobs.double_buffer != 0 && threads == 128 && hdr.T == 11 && !hdr.full && !knobs.bulk && knobs.ptx_ops &&
-              3 * (tile_smem_bytes(hdr, threads, true) + 1024) <= TILE_SMEM_MAX;
-    const tile_kernel_t kern = select_kernel(threads == 256 ? 256 : 128, knobs.ctas_per_sm, hdr.full != 0, knobs.bulk != 0,
+    // Two tile buffers (the next tile is loaded a whole tile of compute ahead): measured no gain, for
+    // local and for peer passes alike -- the exposed wait is not the load's latency -- so only on request.
+    const bool bulk = knobs.bulk > 0 || (knobs.bulk < 0 && hdr.touches_peer);
+    const bool want_db = knobs.double_buffer > 0;
+    bool db = want_db && threads == 128 && hdr.T == 11 && !hdr.full && !bulk && knobs.ptx_ops &&
+              2 * (tile_smem_bytes(hdr, threads, true) + 1024) <= TILE_SMEM_MAX;
+    const tile_kernel_t kern = select_kernel(threads == 256 ? 256 : 128, knobs.ctas_per_sm, hdr.full != 0, bulk,
                                              knobs.ptx_ops != 0, db);
     const size_t smem = tile_smem_bytes(hdr, threads, db);
     if (smem > TILE_SMEM_MAX) return -1;

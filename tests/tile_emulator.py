@@ -17,7 +17,7 @@ import numpy as np
 
 FC_PR, FC_PX, FC_DS, FC_DU, FC_DG, FC_LX, FC_LI, FC_DM, FC_MASKED, FC_SW = 0, 4, 8, 12, 13, 14, 15, 16, 17, 34
 FC_TOTAL = 38
-MOP_SKIP0, MOP_COND, MOP_PARB, MOP_CONDB, MOP_ATHR = 0x02, 0x04, 0x08, 0x10, 0x20
+MOP_SKIP0, MOP_COND, MOP_PARB, MOP_CONDB, MOP_ATHR, MOP_STATIC = 0x02, 0x04, 0x08, 0x10, 0x20, 0x40
 NV = 16
 U64 = (1 << 64) - 1
 
@@ -98,6 +98,13 @@ def run_stage(tile: np.ndarray, st, T: int, gbase: int):
         if code == FC_DM:
             cnt = m.a_reg
             okm = okmask(m, masked)
+            if m.flags & MOP_STATIC:
+                # tabulated run: the kernel takes the thread-bit members' factor from a table built with
+                # vgrp == thread index, and the outside members' factor from a per-tile table
+                assert not any(q.code % FC_TOTAL == FC_LX for q in mops), "a tabulated run needs vgrp == thread index"
+                assert all((e.a_thr != 0) != (e.a_base != 0) for e in mops[i + 1:i + 1 + cnt])
+                assert bool(m.flags & MOP_PARB) == any(e.a_base != 0 for e in mops[i + 1:i + 1 + cnt])
+                assert 0 <= m.a_thr < 12
             acc = np.ones(G, dtype=np.complex128)
             for k in range(1, cnt + 1):
                 e = mops[i + k]
