@@ -611,6 +611,8 @@ int qvnt_reg_clone(qvnt_reg_t *r, qvnt_reg_t **out) {
             b->opt_tile_bits = a->opt_tile_bits;
             b->opt_chunk_bits = a->opt_chunk_bits;
             b->opt_remap = a->opt_remap;
+            b->opt_peer_chunk_bits = a->opt_peer_chunk_bits;
+            b->opt_peer_tile_bits = a->opt_peer_tile_bits;
             b->knobs = a->knobs;
         }
         c->rng_state = r->rng_state;
@@ -1100,6 +1102,14 @@ int qvnt_reg_set_option(qvnt_reg_t *r, const char *key, int64_t value) {
                 s->opt_remap = value != 0;
                 continue;
             }
+            if (!strcmp(key, "peer_chunk_bits")) {
+                s->opt_peer_chunk_bits = (int)value;
+                continue;
+            }
+            if (!strcmp(key, "peer_tile_bits")) {
+                s->opt_peer_tile_bits = (int)value;
+                continue;
+            }
             int rc = qvnt_reg_set_option(s, key, value);
             if (rc) return rc;
         }
@@ -1124,6 +1134,18 @@ int qvnt_reg_set_option(qvnt_reg_t *r, const char *key, int64_t value) {
         if (rc) return rc;
         if (!value && (rc = restore_layout(r))) return rc;
         r->opt_remap = value != 0;
+    } else if (!strcmp(key, "peer_chunk_bits")) {
+        if (value != 0 && (value < 2 || value > TILE_MAX_BITS)) {
+            set_error("peer_chunk_bits must be 0 (same as chunk_bits) or 2..%d", TILE_MAX_BITS);
+            return QVNT_ERR_INVALID;
+        }
+        r->opt_peer_chunk_bits = (int)value;
+    } else if (!strcmp(key, "peer_tile_bits")) {
+        if (value != 0 && (value < 6 || value > TILE_MAX_BITS)) {
+            set_error("peer_tile_bits must be 0 (same as tile_bits) or 6..%d", TILE_MAX_BITS);
+            return QVNT_ERR_INVALID;
+        }
+        r->opt_peer_tile_bits = (int)value;
     } else if (!strcmp(key, "prefetch")) r->knobs.prefetch = value != 0;
     else if (!strcmp(key, "ptx_ops")) r->knobs.ptx_ops = value != 0;
     else if (!strcmp(key, "double_buffer")) r->knobs.double_buffer = value != 0;

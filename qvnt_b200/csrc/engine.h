@@ -129,6 +129,7 @@ constexpr uint8_t MOP_STATIC = 0x40;  // flags bit 6 (FC_DM header): every membe
                                       //   members is tabulated once per kernel (slot = header's a_thr), the factor of the
                                       //   outside members once per tile (MOP_PARB on the header: there are such members)
 constexpr int TILE_MAX_STATIC = 12;   // tabulated runs per pass (2 KiB of shared memory each at 128 threads)
+constexpr uint32_t MOP_END = 255;     // code of the sentinel descriptor the kernel puts behind every stage in shared memory
 constexpr uint32_t MOP_ALT_BYTES = 32; // byte distance from the coefficient block to the `alt` block
 
 struct __align__(16) MOp {   // 80 bytes, staged in shared memory

@@ -17,7 +17,7 @@ SOMETIMES needs is kept off that path:
 Operands of the asm statement (tile.cu, stage_ops_fast_ptx):
   %0..%31  the 16 register-resident amplitudes, v[K].x = %(2K), v[K].y = %(2K+1)      ("+d")
   %32 vgrp  %33 inv  %34 jl  %35 mine_o ("+r")   %36 goff ("+l")
-  %37 first op (shared-window address)  %38 end  %39 this tile's flag bytes
+  %37 first op (shared-window address; a sentinel descriptor ends the stage)  %38 unused  %39 this tile's flag bytes
   %40 this thread's column of the tabulated-run table  %41 this tile's outside-the-tile factors
   %42 byte stride between runs in the table ("r")
 
@@ -136,6 +136,8 @@ def gen():
     # first-level table: masked arms go through $MPRE; classes 1 / 2 (code + 38, + 76) through the stubs
     t1 = [("$MPRE" if (FC_MASKED <= c and arm[c] != "$TOP") else arm[c]) for c in range(FC_TOTAL)]
     tbl = t1 + ["$C1"] * FC_TOTAL + ["$C2"] * FC_TOTAL
+    tbl += ["$TOP"] * (256 - len(tbl))
+    tbl[255] = "$END"                    # the sentinel descriptor behind every stage (engine.h MOP_END)
     # the lazy x forms are a handful of instructions: they test their thread controls themselves
     # (ctrl_thr is 0 for an unconditional one) instead of paying a second indirect jump
     tbl[FC_TOTAL + FC_LX] = "$LX"
@@ -155,8 +157,6 @@ def gen():
     e("ld.shared.v4.u32 {h0, h1, h2, h3}, [p];")
     # ---- per-op prologue ----
     e("$TOP:")
-    e("setp.eq.u32 pq, p, %38;")
-    e("@pq bra.uni $END;")
     e("mov.u32 w0, h0;")
     e("mov.u32 w1, h1;")
     e("and.b32 code, w0, 255;")

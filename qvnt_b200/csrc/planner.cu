@@ -43,6 +43,10 @@ struct PlanCfg {
     int tile_bits, chunk_bits;
     uint8_t perm[64];        // logical qubit -> physical index bit at the start of the op list
     uint64_t ack_cap = ~0ull; // tiles the per-tile handshake array of a remap pass can hold
+    int peer_chunk_bits = 0;  // chunk size of passes that START on a global qubit (0 = same as chunk_bits): larger
+                              // contiguous runs make better NVLink requests
+    int peer_tile_bits = 0;   // tile size of those passes (0 = same as tile_bits): more gathered bits carry more
+                              // gates per NVLink exchange
     int force_pinned = -1;    // restore_layout: the local bit a remap pass must trade the global bit with
     uint64_t q_mask() const { return q_num >= 64 ? ~0ull : ((1ull << q_num) - 1ull); }
 };
@@ -447,12 +451,23 @@ static int build_plan(const PlanCfg &c, std::vector<POp> &pl, Plan &plan) {
         }
         uint64_t set = 0;
         const uint64_t allowed = peers ? qmask : lmask;
+        // passes that start on a global qubit may use larger chunks (option "peer_chunk_bits")
+        uint32_t Lp = L, Tp = T;
+        if (first_global && c.force_pinned < 0) {
+            if (c.peer_tile_bits > (int)T) Tp = (uint32_t)c.peer_tile_bits;
+            if (Tp > (uint32_t)TILE_MAX_BITS) Tp = TILE_MAX_BITS;
+            if (Tp > n_local) Tp = n_local;
+            if (c.peer_chunk_bits > (int)L) Lp = (uint32_t)c.peer_chunk_bits;
+            if (Lp + 2 > Tp) Lp = Tp - 2;
+            if (Tp - Lp > (uint32_t)TILE_MAX_HIGH) Lp = Tp - TILE_MAX_HIGH;
+        }
+        const uint64_t low_p = (1ull << Lp) - 1ull;
         if (!c.fuse) {
             sel.assign(1, cand[0]);
             rest.assign(cand.begin() + 1, cand.end());
-            set = low | first.mix;
+            set = low_p | first.mix;
         } else {
-            greedy_select(pl, cand, low, allowed, (int)(T - L), qmask, 1u << 16, sel, rest, set);
+            greedy_select(pl, cand, low_p, allowed, (int)(Tp - Lp), qmask, 1u << 16, sel, rest, set);
         }
         if (sel.empty() && !first_global) {
             // no tile geometry holds the op's mix bits (tiny shards): one direct sweep
@@ -475,12 +490,12 @@ static int build_plan(const PlanCfg &c, std::vector<POp> &pl, Plan &plan) {
             continue;
         }
         // fill the tile up to T bits with the lowest unused local bits (keeps it contiguous)
-        for (uint32_t b = L; pc64(set) < (int)T && b < n_local; ++b)
+        for (uint32_t b = Lp; pc64(set) < (int)Tp && b < n_local; ++b)
             if ((int)b != c.force_pinned) set |= 1ull << b;
         // tile-local numbering: ascending global position
         TPassHdr &h = pp.hdr;
         h.T = (uint32_t)pc64(set);
-        h.L = L;
+        h.L = Lp;
         uint32_t lp = 0;
         for (uint64_t m = set; m; m &= m - 1) h.gpos[lp++] = (uint8_t)ctz64(m);
         const uint64_t tile_g = set & gmask;
@@ -1032,6 +1047,8 @@ static PlanCfg cfg_of(const qvnt_reg *r) {
     c.tile_bits = r->opt_tile_bits;
     c.chunk_bits = r->opt_chunk_bits;
     c.remap = r->opt_remap != 0 && r->remap_possible;
+    c.peer_chunk_bits = r->opt_peer_chunk_bits;
+    c.peer_tile_bits = r->opt_peer_tile_bits;
     c.ack_cap = r->ack_cap;
     memcpy(c.perm, r->perm, sizeof(c.perm));
     return c;
@@ -1244,6 +1261,8 @@ int describe_plan(uint32_t q_num, uint32_t rank, uint32_t world, int peers, int 
     c.n_local = q_num - wb;
     c.peers = peers != 0;
     c.remap = !(peers & 2);          // (peers_attached == 3: peers attached, remap passes off)
+    c.peer_chunk_bits = tile_bits ? 0 : 6;     // the library defaults (reg.h) unless the caller fixes the geometry
+    c.peer_tile_bits = tile_bits ? 0 : 12;
     for (uint32_t q = 0; q < 64; ++q) c.perm[q] = (uint8_t)q;
     c.fuse = fuse != 0;
     c.tile_bits = tile_bits;

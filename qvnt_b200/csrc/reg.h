@@ -33,6 +33,8 @@ struct qvnt_reg {
     void *peer_ack[qv::MAX_WORLD] = {};
     uint32_t remap_epoch = 0;
     int opt_remap = 1;
+    int opt_peer_chunk_bits = 6;    // passes that start on a global qubit: 1 KiB chunks, 2^12-amplitude tiles (measured at 4 GPUs:
+    int opt_peer_tile_bits = 12;    // +26 % over the local-pass geometry)
     bool remap_possible = false;            // one GPU per shard (set by attach_peers)
 
     // scratch (device)

@@ -749,8 +749,8 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     unsigned char *tile_b = smem_raw;                                              // (DB ? 2 : 1) * n_chunks * (16 * 2^L + 16)
     const uint32_t bufs_bytes = DB ? 2u * buf_bytes : buf_bytes;
     unsigned long long *s_mbar = reinterpret_cast<unsigned long long *>(smem_raw + bufs_bytes);   // 16
-    MOp *s_ops = reinterpret_cast<MOp *>(smem_raw + bufs_bytes + 16u);             // 80 * n_ops
-    TStage *s_stages = reinterpret_cast<TStage *>(s_ops + n_ops);                  // 32 * n_stages
+    MOp *s_ops = reinterpret_cast<MOp *>(smem_raw + bufs_bytes + 16u);             // 80 * (n_ops + n_stages)
+    TStage *s_stages = reinterpret_cast<TStage *>(s_ops + n_ops + n_stages);       // 32 * n_stages
     MBase *s_bases = reinterpret_cast<MBase *>(s_stages + n_stages);               // 16 * n_ops
     const uint32_t n_bases = (FULL || hdr.need_flags) ? n_ops : 0u;                 // (per-tile flags only)
     unsigned long long *s_ptr0 = reinterpret_cast<unsigned long long *>(s_bases + n_bases);   // 8 * n_chunks
@@ -764,15 +764,25 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     const uint32_t flags_bytes = need_flags_smem(hdr, FULL) ? META_SLOTS * flags_stride : 16u;
     double2 *s_dtab = reinterpret_cast<double2 *>(s_flags_all + flags_bytes);      // 16 * nthr * n_static
     double2 *s_dout = s_dtab + (size_t)nthr * n_static;                            // 16 * META_SLOTS * n_static
+    uint32_t *s_runhdr = reinterpret_cast<uint32_t *>(s_dout + META_SLOTS * n_static);   // 4 * n_static: op index of each run's header
 
     const uint32_t shard_shift = segs.shift;
     const uint64_t shard_mask = (1ull << shard_shift) - 1ull;
     const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(s_mbar);
     // the pass program: same for every tile this CTA processes
     {
+        // Stage s's descriptors sit at s_ops[op index + s]: one SENTINEL descriptor (code MOP_END) follows
+        // every stage, so the op loop needs neither an end pointer nor a compare -- it jumps on the code.
         const uint4 *src = reinterpret_cast<const uint4 *>(g_ops + hdr.op_begin);
         uint4 *dst = reinterpret_cast<uint4 *>(s_ops);
-        for (uint32_t i = tid; i < (MOP_BYTES / 16u) * n_ops; i += nthr) dst[i] = src[i];
+        for (uint32_t i = tid; i < (MOP_BYTES / 16u) * n_ops; i += nthr) {
+            const uint32_t o = i / (MOP_BYTES / 16u);
+            uint32_t sh = 0;
+            while (sh < n_stages && o >= hdr.stage_end[sh]) ++sh;
+            dst[i + sh * (MOP_BYTES / 16u)] = src[i];
+        }
+        for (uint32_t st = tid; st < n_stages; st += nthr)
+            dst[(hdr.stage_end[st] + st) * (MOP_BYTES / 16u)] = make_uint4(MOP_END, 0u, 0u, 0u);
         src = reinterpret_cast<const uint4 *>(g_stages + hdr.stage_begin);
         dst = reinterpret_cast<uint4 *>(s_stages);
         for (uint32_t i = tid; i < 2 * n_stages; i += nthr) dst[i] = src[i];
@@ -811,8 +821,9 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     }
     if (!FULL && n_static) {
         // factor of every tabulated run's thread-bit members for THIS thread (its group number is its index)
-        for (uint32_t o = 0; o < n_ops; ++o) {
+        for (uint32_t o = 0; o < n_ops + n_stages; ++o) {        // (shared-memory positions: sentinels included)
             const MOp &hd = s_ops[o];
+            if (hd.code == (uint8_t)MOP_END) continue;
             const uint32_t base_code = hd.code % (uint32_t)FC_TOTAL;
             if ((base_code != (uint32_t)FC_DM && base_code != (uint32_t)(FC_DM + FC_MASKED)) || !(hd.dagger & MOP_STATIC)) continue;
             double ar = 1.0, ai = 0.0;
@@ -827,6 +838,10 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
                 ar = t;
             }
             s_dtab[hd.a_thr * nthr + tid] = make_double2(ar, ai);
+            if (tid == 0) {
+                s_runhdr[2u * hd.a_thr] = o;                   // position in shared memory
+                s_runhdr[2u * hd.a_thr + 1u] = hd.idx;         // op index (s_bases, flags)
+            }
             o += hd.a_reg;
         }
     }
@@ -881,26 +896,36 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
                 const uint32_t okb = ((~gb & b.ctrl_base) == 0) ? 0x80u : 0u;
                 flags[o] = (uint8_t)(okb | ((uint32_t)__popcll(gb & b.a_base) & 7u));
                 any |= (int)okb;
-                if (!FULL && n_static) {
+            }
+            if (!FULL && n_static) {
+                // this tile's factor of every tabulated run's members OUTSIDE the tile: one warp per run,
+                // one member per lane, product by shuffles (a serial walk by one thread cost a third of a
+                // QFT pass: every other thread waits for it at the barrier below)
+                const uint32_t lane = tid & 31u, nw = nthr >> 5;
+                for (uint32_t r = tid >> 5; r < n_static; r += nw) {
+                    const uint32_t o = s_runhdr[2u * r], ob = s_runhdr[2u * r + 1u];
                     const MOp &hd = s_ops[o];
-                    const uint32_t base_code = hd.code % (uint32_t)FC_TOTAL;
-                    if ((base_code == (uint32_t)FC_DM || base_code == (uint32_t)(FC_DM + FC_MASKED)) &&
-                        (hd.dagger & MOP_STATIC) && (hd.dagger & MOP_PARB)) {
-                        // this tile's factor of the run's members outside the tile
-                        double ar = 1.0, ai = 0.0;
-                        for (uint32_t k = 1; k <= hd.a_reg; ++k) {
-                            const uint64_t ab = s_bases[o + k].a_base;
-                            if (!ab) continue;
-                            const MOp &m = s_ops[o + k];
-                            const uint32_t par = (uint32_t)__popcll(gb & ab) & 1u;
-                            if (!par && (m.dagger & MOP_SKIP0)) continue;
-                            const double fr = par ? m.c2 : m.ph_re, fi = par ? m.c3 : m.ph_im;
-                            const double t = ar * fr - ai * fi;
-                            ai = ar * fi + ai * fr;
-                            ar = t;
-                        }
-                        s_dout[slot * n_static + hd.a_thr] = make_double2(ar, ai);
+                    if (!(hd.dagger & MOP_PARB)) continue;
+                    double ar = 1.0, ai = 0.0;
+                    for (uint32_t k = 1 + lane; k <= hd.a_reg; k += 32u) {
+                        const uint64_t ab = s_bases[ob + k].a_base;
+                        if (!ab) continue;
+                        const MOp &m = s_ops[o + k];
+                        const uint32_t par = (uint32_t)__popcll(gb & ab) & 1u;
+                        if (!par && (m.dagger & MOP_SKIP0)) continue;
+                        const double fr = par ? m.c2 : m.ph_re, fi = par ? m.c3 : m.ph_im;
+                        const double t = ar * fr - ai * fi;
+                        ai = ar * fi + ai * fr;
+                        ar = t;
                     }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const double br = __shfl_down_sync(0xffffffffu, ar, off), bi = __shfl_down_sync(0xffffffffu, ai, off);
+                        const double t = ar * br - ai * bi;
+                        ai = ar * bi + ai * br;
+                        ar = t;
+                    }
+                    if (lane == 0) s_dout[slot * n_static + r] = make_double2(ar, ai);
                 }
             }
             if (remap) any = 1;                          // every tile moves
@@ -1037,13 +1062,13 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
             }
             if (active) {
                 uint32_t inv = 0;
-                if (FULL) stage_ops_full(ops_s, flags_s, ob, oe, tid, mats, v);
+                if (FULL) stage_ops_full(ops_s + MOP_BYTES * s, flags_s, ob, oe, tid, mats, v);
                 else if (PTXOPS)
-                    stage_ops_fast_ptx(ops_s, flags_s, ob, oe, tid, x, inv, v,
+                    stage_ops_fast_ptx(ops_s + MOP_BYTES * s, flags_s, ob, oe, tid, x, inv, v,
                                        (uint32_t)__cvta_generic_to_shared(s_dtab + tid), 16u * nthr,
                                        (uint32_t)__cvta_generic_to_shared(s_dout + mslot * n_static));
                 else
-                    stage_ops_fast(reinterpret_cast<const unsigned char *>(s_ops), flags, ob, oe, tid, L, x, inv, v,
+                    stage_ops_fast(reinterpret_cast<const unsigned char *>(s_ops + s), flags, ob, oe, tid, L, x, inv, v,
                                    s_dtab + tid, nthr, s_dout + mslot * n_static);
                 if (!last) stage_store_smem(tile_s, x, inv, v);
                 else if (hdr.touches_peer && !remap) stage_store_global(ptr0_s, L, toff_cur, x, inv, v);
@@ -1067,11 +1092,11 @@ constexpr size_t TILE_SMEM_MAX = 227u * 1024u;
 
 static size_t tile_smem_bytes(const TPassHdr &h, int threads, bool db = false) {
     const bool flags = h.full || h.need_flags;
-    return (db ? 2 : 1) * (((size_t)16 << h.T) + ((size_t)16 << (h.T - h.L))) + 16 + (size_t)MOP_BYTES * h.n_ops +
+    return (db ? 2 : 1) * (((size_t)16 << h.T) + ((size_t)16 << (h.T - h.L))) + 16 + (size_t)MOP_BYTES * (h.n_ops + h.n_stages) +
            (flags ? sizeof(MBase) * h.n_ops : 0) + (size_t)32 * h.n_stages + (((size_t)8 << (h.T - h.L)) + 8) +
            (size_t)16 * h.n_stages + (size_t)4 * threads * h.n_stages + 16 +
            (flags ? (size_t)META_SLOTS * ((h.n_ops + 15u) & ~15u) : 16) +
-           (size_t)16 * h.n_static * ((size_t)threads + META_SLOTS);
+           (size_t)16 * h.n_static * ((size_t)threads + META_SLOTS) + (size_t)8 * h.n_static;
 }
 
 typedef void (*tile_kernel_t)(const Segs, const TPassHdr, const TStage *, const MOp *, const MBase *, const amp *);
