@@ -182,7 +182,10 @@ int qvnt_reg_sync(qvnt_reg_t *reg);
  * auto, 3..5 CTAs per SM for 2^11-amplitude tiles); "ptx_ops" (1, default: the fast interpreter's
  * op loop as one inline-PTX block; 0: the C++ loop); "remap" (1, default: a pass on a global qubit
  * leaves it local -- logical -> physical qubit map; 0: exchange and write back);
- * "double_buffer", "prefetch" (experiments, off); "profile" (0/1: time every launch with CUDA
+ * "peer_chunk_bits", "peer_tile_bits" (the same two sizes for passes that start on a global
+ * qubit); "single_ctrl" (1, default: diagonal ops with one control in a register slot run
+ * through their own arms; 0: the generic predicated ones); "double_buffer" (0; 1: two tile buffers
+ * per CTA, 2: only for passes that read a peer shard), "prefetch" (experiments, off); "profile" (0/1: time every launch with CUDA
  * events); "seed". */
 int qvnt_reg_set_option(qvnt_reg_t *reg, const char *key, int64_t value);
 int qvnt_reg_stats(qvnt_reg_t *reg, qvnt_stats_t *out);

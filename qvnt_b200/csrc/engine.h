@@ -111,12 +111,28 @@ enum FCode : uint8_t {
     FC_MASKED = 17, // added to FC_PR / FC_PX / FC_DS / FC_DU / FC_DG / FC_DM codes when a control sits in a
                     // register slot (okmask != 0xFFFF): per-slot-pattern predicates
     FC_SW = 34,   // + slot (always masked)
-    FC_TOTAL = 38
+    FC_TOTAL = 38,
     // The code byte of a fast MOp also carries the op's CONTROL CLASS: code = arm + FC_TOTAL * cls,
     // cls 0: unconditional, 1: controls on thread bits, 2: ... and outside the tile (MOP_COND /
-    // MOP_CONDB say the same).  The PTX op loop jumps on the whole byte (classes 1 / 2 land in a stub
-    // that tests the controls first), so unconditional ops never pay for the test.
+    // MOP_CONDB say the same).  The PTX op loop jumps on the whole byte (class 1 lands in a stub that
+    // tests the controls first; class 2 is rewritten per tile, tile.cu patch_codes), so
+    // unconditional ops never pay for the test.
+    //
+    // SINGLE-CONTROL arms (bytes 3 * FC_TOTAL .. FC_SPECIAL_END - 1, class 0 only): diagonal forms whose
+    // ONLY control sits in register slot c (qft's controlled phases).  The generic masked arms test a
+    // predicate per slot pattern -- ptxas turns that into all the arithmetic plus a select per result,
+    // 3x the instructions of the unmasked arm; these touch exactly the 8 patterns with bit c set.
+    FC_DS1 = 114, // + 4 * j + c: FC_MASKED + FC_DS + j with okmask == "slot bit c set"
+    FC_DU1 = 130, // + c: FC_MASKED + FC_DU
+    FC_DM1 = 134, // + c: FC_MASKED + FC_DM
+    FC_SPECIAL_END = 138
 };
+// the generic (masked) code a single-control byte stands for; any other byte unchanged
+__host__ __device__ inline uint32_t fc_generic(uint32_t byte) {
+    if (byte < (uint32_t)FC_DS1 || byte >= (uint32_t)FC_SPECIAL_END) return byte;
+    if (byte < (uint32_t)FC_DU1) return (uint32_t)(FC_MASKED + FC_DS) + ((byte - (uint32_t)FC_DS1) >> 2);
+    return byte < (uint32_t)FC_DM1 ? (uint32_t)(FC_MASKED + FC_DU) : (uint32_t)(FC_MASKED + FC_DM);
+}
 constexpr uint8_t MOP_SKIP0 = 0x02;   // flags bit 1 (diagonal forms): f0 == 1, even parity untouched
 constexpr uint8_t MOP_COND = 0x04;    // flags bit 2: the op has controls on thread bits or outside the tile
                                       //   (ctrl_thr != 0 or ctrl_base != 0): test before dispatch
@@ -130,6 +146,9 @@ constexpr uint8_t MOP_STATIC = 0x40;  // flags bit 6 (FC_DM header): every membe
                                       //   outside members once per tile (MOP_PARB on the header: there are such members)
 constexpr int TILE_MAX_STATIC = 12;   // tabulated runs per pass (2 KiB of shared memory each at 128 threads)
 constexpr uint32_t MOP_END = 255;     // code of the sentinel descriptor the kernel puts behind every stage in shared memory
+constexpr uint32_t MOP_NOP = 254;     // PTX op loop: code the kernel writes over a class-2 op whose controls outside the tile are
+                                      //   not satisfied in the CURRENT tile (a satisfied one gets its class 0 / 1 code)
+constexpr uint32_t MOP_NOP_RUN = 253; // ... the same for a merged run's header: its members are skipped with it
 constexpr uint32_t MOP_ALT_BYTES = 32; // byte distance from the coefficient block to the `alt` block
 
 struct __align__(16) MOp {   // 80 bytes, staged in shared memory
@@ -202,7 +221,8 @@ struct TileKnobs {
                            //    2 GPUs), cp.async for local passes (a 256-byte bulk copy costs its issuing lane ~17
                            //    instructions: measured -8 % on one GPU)
     int prefetch = 0;      // 1: cp.async.bulk.prefetch.L2 of tile i+1 while tile i computes (measured: no gain, off)
-    int double_buffer = 0; // 1: two tile buffers per CTA (2^11 tiles, cp.async loads); measured no gain, local or peer: off
+    int double_buffer = 0; // 1: two tile buffers per CTA (2^11 tiles); 2: only for passes that read a peer shard
+    int single_ctrl = 1;   // planner: single-control arms (FC_DS1 / FC_DU1 / FC_DM1) instead of the generic masked ones
     int ptx_ops = 1;       // 1: the fast interpreter's op loop as one inline-PTX block (fastops_ptx.inc); 0: C++ loop
 };
 int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, const TStage *d_stages,

@@ -7,8 +7,11 @@ Why PTX: the C++ switch compiles to a compare tree plus divergence bookkeeping (
 by hand, an unconditional op costs: the (prefetched) header, two coefficient loads, the jump-table
 load and the indirect branch -- ~17 instructions -- and the FP64 body.  Everything an op only
 SOMETIMES needs is kept off that path:
-  * controls on thread bits / outside the tile: the op's code carries a class (code = arm + 38 * cls),
-    classes 1 / 2 jump to a stub that tests the controls and re-dispatches (or skips the op);
+  * controls on thread bits: the op's code carries a class (code = arm + 38 * cls), class 1 jumps to a
+    stub that tests the controls and re-dispatches (or skips the op);
+  * controls outside the tile (class 2) are the same for the whole tile: before a tile's first stage
+    the kernel rewrites those code bytes into the class 0 / 1 code or a skip code (tile.cu, patch_codes),
+    so the loop never sees them;
   * controls in register slots (okmask): the masked arms are reached through a stub that builds the
     predicate mask (and permutes it by the inverted slots);
   * diagonal ops with target bits outside the register slots, merged runs, lazy x: the arm re-reads the
@@ -28,14 +31,24 @@ import sys
 
 NV = 16
 FC_PR, FC_PX, FC_DS, FC_DU, FC_DG, FC_LX, FC_LI, FC_DM, FC_MASKED, FC_SW, FC_TOTAL = 0, 4, 8, 12, 13, 14, 15, 16, 17, 34, 38
+FC_DS1, FC_DU1, FC_DM1 = 114, 130, 134      # one control in register slot c, no other control (engine.h)
 SKIP0, COND, PARB, CONDB, ATHR, STATIC = 0x02 << 8, 0x04 << 8, 0x08 << 8, 0x10 << 8, 0x20 << 8, 0x40 << 8
 MOP = 80
 
+# Code layout: the arms a random circuit keeps jumping between (pairs, unmasked diagonals, lazy x, the
+# controlled swaps) are emitted first and stay together behind the prologue (the SM's instruction
+# cache holds 32 KB); then the arms of qft-like circuits; the generic predicated arms come last.
 L = []
+SECT = {"hot": [], "warm": [], "cold": []}
+CUR = ["hot"]
 
 
 def e(s=""):
-    L.append(s)
+    SECT[CUR[0]].append(s)
+
+
+def sect(name):
+    CUR[0] = name
 
 
 def X(K):
@@ -135,8 +148,18 @@ def gen():
     arm[FC_MASKED + FC_DM] = "$MDM"
     # first-level table: masked arms go through $MPRE; classes 1 / 2 (code + 38, + 76) through the stubs
     t1 = [("$MPRE" if (FC_MASKED <= c and arm[c] != "$TOP") else arm[c]) for c in range(FC_TOTAL)]
-    tbl = t1 + ["$C1"] * FC_TOTAL + ["$C2"] * FC_TOTAL
+    # class 2 (controls outside the tile) never reaches the loop: the kernel rewrites those code bytes
+    # for every tile (tile.cu, patch_codes) into the class 0 / 1 code or one of the two skip codes
+    tbl = t1 + ["$C1"] * FC_TOTAL + ["$TOP"] * FC_TOTAL
     tbl += ["$TOP"] * (256 - len(tbl))
+    for c in range(4):
+        for j in range(4):
+            if j != c:
+                tbl[FC_DS1 + 4 * j + c] = f"$DS{j}c{c}"
+        tbl[FC_DU1 + c] = f"$DUc{c}"
+        tbl[FC_DM1 + c] = f"$DMc{c}"
+    tbl[253] = "$SKIPRUN"                # engine.h MOP_NOP_RUN: a switched-off run header takes its members with it
+    tbl[254] = "$TOP"                    # engine.h MOP_NOP: an op this tile's outside controls switch off
     tbl[255] = "$END"                    # the sentinel descriptor behind every stage (engine.h MOP_END)
     # the lazy x forms are a handful of instructions: they test their thread controls themselves
     # (ctrl_thr is 0 for an unconditional one) instead of paying a second indirect jump
@@ -145,7 +168,7 @@ def gen():
 
     e("{")
     e(".reg .pred pq, pb, pk, pz, pa;")
-    e(".reg .u32 p, w0, w1, w2, w3, h0, h1, h2, h3, code, t, u, blk, ca, ok, fl, cnt, par, lo, hi, areg, ib;")
+    e(".reg .u32 p, w0, w1, w2, w3, h0, h1, code, t, u, blk, ca, ok, fl, cnt, par, lo, hi, areg, ib, dmv;")
     e(".reg .f64 c0, c1, c2, c3, ta, tb, tc, td, n1, n2, ar, ai, fr, fi;")
     e(".reg .u64 g64;")
     e("$TBL: .branchtargets " + ", ".join(tbl) + ";")
@@ -154,20 +177,22 @@ def gen():
     e("mov.u32 ok, 65535;")
     # The header of op k+1 is fetched while op k runs (h*).  (The fetch behind the stage's last op
     # reads the next descriptor or the table after the op array -- inside the CTA's shared memory.)
-    e("ld.shared.v4.u32 {h0, h1, h2, h3}, [p];")
+    e("ld.shared.v2.u32 {h0, h1}, [p];")
     # ---- per-op prologue ----
     e("$TOP:")
     e("mov.u32 w0, h0;")
     e("mov.u32 w1, h1;")
+    # (ptxas sinks this add behind the loads whatever the order here, and the add then waits until the
+    # loads have read their address register: 2.4 % of the kernel's samples; a run-time step was no better)
+    e(f"add.u32 p, p, {MOP};")
     e("and.b32 code, w0, 255;")
     e("and.b32 t, w0, 3;")                 # the op's register slot is code & 3: its inversion byte (0 / 32)
     e("or.b32 t, t, 0x4440;")              # picks the coefficient block (the alt block while inverted)
     e("prmt.b32 blk, %33, 0, t;")
+    e("ld.shared.v2.u32 {h0, h1}, [p];")
     e("add.u32 ca, p, blk;")
-    e("ld.shared.v2.f64 {c0, c1}, [ca+16];")
-    e("ld.shared.v2.f64 {c2, c3}, [ca+32];")
-    e(f"ld.shared.v4.u32 {{h0, h1, h2, h3}}, [p+{MOP}];")
-    e(f"add.u32 p, p, {MOP};")
+    e(f"ld.shared.v2.f64 {{c0, c1}}, [ca+{16 - MOP}];")
+    e(f"ld.shared.v2.f64 {{c2, c3}}, [ca+{32 - MOP}];")
     e("brx.idx.uni code, $TBL;")
     # ---- class 1: controls on thread bits ----
     e("$C1:")
@@ -177,31 +202,17 @@ def gen():
     e("setp.ne.u32 pk, t, 0;")
     e("@pk bra $SKIP;")
     e("brx.idx.uni code, $TBL;")
-    # ---- class 2: ... and controls outside the tile (this tile's flag byte, bit 7) ----
-    e("$C2:")
-    e(f"sub.u32 code, code, {2 * FC_TOTAL};")
-    reload()
-    e("shr.u32 u, w3, 16;")
-    e("add.u32 u, u, %39;")
-    e("ld.shared.u8 fl, [u];")
-    e("not.b32 t, %32;")
-    e("and.b32 t, t, w1;")
-    e("and.b32 u, fl, 128;")
-    e("setp.ne.u32 pk, t, 0;")
-    e("setp.eq.u32 pb, u, 0;")
-    e("or.pred pk, pk, pb;")
-    e("@pk bra $SKIP;")
-    e("brx.idx.uni code, $TBL;")
     # a skipped run header takes its members with it
     e("$SKIP:")
     e(f"setp.eq.u32 pk, code, {FC_DM};")
     e(f"setp.eq.u32 pb, code, {FC_DM + FC_MASKED};")
     e("or.pred pk, pk, pb;")
     e("@!pk bra $TOP;")
+    e("$SKIPRUN:")
     reload()
     e("and.b32 cnt, w3, 65535;")
     e(f"mad.lo.u32 p, cnt, {MOP}, p;")
-    e("ld.shared.v4.u32 {h0, h1, h2, h3}, [p];")
+    e("ld.shared.v2.u32 {h0, h1}, [p];")
     e("bra $TOP;")
     # ---- controls in register slots: okmask, permuted by the inverted slots (register K holds pattern K ^ ib)
     e("$MPRE:")
@@ -223,6 +234,7 @@ def gen():
     # ---- pair arms ----
     for masked in (False, True):
         pre = "M" if masked else ""
+        sect("cold" if masked else "hot")
         for j in range(4):
             b = 1 << j
             e(f"${pre}PR{j}:")
@@ -241,6 +253,7 @@ def gen():
                 g = pred(K, masked)
                 pair_cross(K, K | b, g)
             e("bra.uni $TOP;")
+    sect("hot")
     for j in range(4):
         b = 1 << j
         e(f"$SW{j}:")
@@ -252,56 +265,77 @@ def gen():
         e("bra.uni $TOP;")
 
     # ---- diagonal, one target bit in register slot j ----
+    def ds_arm(lab, j, masked, only=None):
+        """only = c: the single-control form -- slot patterns with bit c set, no predicates"""
+        b = 1 << j
+        keep = (lambda K: True) if only is None else (lambda K: bool(K & (1 << only)))
+        e(f"${lab}:")
+        if only is not None:
+            # the control's slot inverted by a lazy x: the generic masked arm permutes the predicates
+            e(f"and.b32 t, %33, {0xFF << (8 * only)};")
+            e("setp.ne.u32 pk, t, 0;")
+            e(f"@pk bra $FBDS{j};")
+        # target bits outside the register slots (rzz's second bit, bits outside the tile): their
+        # parity exchanges the roles of f0 and f1 -- the other coefficient block
+        e(f"and.b32 u, w0, {PARB | ATHR};")
+        e("setp.eq.u32 pk, u, 0;")
+        e(f"@pk bra.uni ${lab}g;")
+        reload()
+        dpar()
+        e("setp.eq.u32 pk, par, 0;")
+        e(f"@pk bra ${lab}g;")
+        e("xor.b32 blk, blk, 32;")
+        e(f"sub.u32 ca, p, {MOP};")
+        e("add.u32 ca, ca, blk;")
+        e("ld.shared.v2.f64 {c0, c1}, [ca+16];")
+        e("ld.shared.v2.f64 {c2, c3}, [ca+32];")
+        e(f"${lab}g:")
+        # MOP_SKIP0: the ORIGINAL f0 is 1 -- with the roles exchanged it sits in (c2, c3)
+        e(f"and.b32 u, w0, {SKIP0};")
+        e("setp.ne.u32 pk, u, 0;")
+        e("setp.eq.u32 pz, blk, 0;")
+        e("and.pred pa, pk, pz;")
+        e(f"@pa bra ${lab}b;")
+        e("neg.f64 n1, c1;")
+        for K in range(NV):
+            if (K & b) or not keep(K):
+                continue
+            g = pred(K, masked)
+            cmul(K, "c0", "c1", "n1", g)
+        e(f"${lab}b:")
+        e(f"and.b32 u, w0, {SKIP0};")
+        e("setp.ne.u32 pk, u, 0;")
+        e("setp.ne.u32 pz, blk, 0;")
+        e("and.pred pa, pk, pz;")
+        e("@pa bra $TOP;")
+        e("neg.f64 n2, c3;")
+        for K in range(NV):
+            if not (K & b) or not keep(K):
+                continue
+            g = pred(K, masked)
+            cmul(K, "c2", "c3", "n2", g)
+        e("bra.uni $TOP;")
+
     for masked in (False, True):
-        pre = "M" if masked else ""
+        sect("cold" if masked else "hot")
         for j in range(4):
-            b = 1 << j
-            e(f"${pre}DS{j}:")
-            # target bits outside the register slots (rzz's second bit, bits outside the tile): their
-            # parity exchanges the roles of f0 and f1 -- the other coefficient block
-            e(f"and.b32 u, w0, {PARB | ATHR};")
-            e("setp.eq.u32 pk, u, 0;")
-            e(f"@pk bra.uni ${pre}DS{j}g;")
-            reload()
-            dpar()
-            e("setp.eq.u32 pk, par, 0;")
-            e(f"@pk bra ${pre}DS{j}g;")
-            e("xor.b32 blk, blk, 32;")
-            e(f"sub.u32 ca, p, {MOP};")
-            e("add.u32 ca, ca, blk;")
-            e("ld.shared.v2.f64 {c0, c1}, [ca+16];")
-            e("ld.shared.v2.f64 {c2, c3}, [ca+32];")
-            e(f"${pre}DS{j}g:")
-            # MOP_SKIP0: the ORIGINAL f0 is 1 -- with the roles exchanged it sits in (c2, c3)
-            e(f"and.b32 u, w0, {SKIP0};")
-            e("setp.ne.u32 pk, u, 0;")
-            e("setp.eq.u32 pz, blk, 0;")
-            e("and.pred pa, pk, pz;")
-            e(f"@pa bra ${pre}DS{j}b;")
-            e("neg.f64 n1, c1;")
-            for K in range(NV):
-                if K & b:
-                    continue
-                g = pred(K, masked)
-                cmul(K, "c0", "c1", "n1", g)
-            e(f"${pre}DS{j}b:")
-            e(f"and.b32 u, w0, {SKIP0};")
-            e("setp.ne.u32 pk, u, 0;")
-            e("setp.ne.u32 pz, blk, 0;")
-            e("and.pred pa, pk, pz;")
-            e("@pa bra $TOP;")
-            e("neg.f64 n2, c3;")
-            for K in range(NV):
-                if not (K & b):
-                    continue
-                g = pred(K, masked)
-                cmul(K, "c2", "c3", "n2", g)
-            e("bra.uni $TOP;")
+            ds_arm(("M" if masked else "") + f"DS{j}", j, masked)
+    sect("warm")
+    for j in range(4):
+        for c in range(4):
+            if c != j:
+                ds_arm(f"DS{j}c{c}", j, False, only=c)
+        e(f"$FBDS{j}:")
+        e(f"mov.u32 code, {FC_MASKED + FC_DS + j};")
+        e("bra $MPRE;")
 
     # ---- diagonal, no target bit in a register slot: one factor per thread ----
-    for masked in (False, True):
-        pre = "M" if masked else ""
-        e(f"${pre}DU:")
+    def du_arm(lab, masked, only=None):
+        e(f"${lab}:")
+        if only is not None:
+            e(f"and.b32 t, %33, {0xFF << (8 * only)};")
+            e("setp.ne.u32 pk, t, 0;")
+            e("@pk bra $FBDU;")
         reload()
         dpar()
         e(f"and.b32 u, w0, {SKIP0};")
@@ -315,11 +349,25 @@ def gen():
         e("ld.shared.v2.f64 {fr, fi}, [ca];")
         e("neg.f64 n1, fi;")
         for K in range(NV):
+            if only is not None and not (K & (1 << only)):
+                continue
             g = pred(K, masked)
             cmul(K, "fr", "fi", "n1", g)
         e("bra.uni $TOP;")
 
+    sect("hot")
+    du_arm("DU", False)
+    sect("cold")
+    du_arm("MDU", True)
+    sect("warm")
+    for c in range(4):
+        du_arm(f"DUc{c}", False, only=c)
+    e("$FBDU:")
+    e(f"mov.u32 code, {FC_MASKED + FC_DU};")
+    e("bra $MPRE;")
+
     # ---- diagonal, any set of target bits in register slots (always dispatched as masked) ----
+    sect("cold")
     e("$DG:")
     reload()
     dpar()
@@ -346,6 +394,7 @@ def gen():
         cmul(K, "fr", "fi", "n1", g)
     e("bra.uni $TOP;")
 
+    sect("hot")
     # ---- lazy x: target on a thread bit (c0 = smem delta | bit << 32, c1 = shard-offset delta,
     #      c2 = the target's thread bit) ----
     e("$LX:")
@@ -376,67 +425,103 @@ def gen():
     e("bra.uni $TOP;")
 
     # ---- merged diagonal run: header + cnt members (FC_DU forms sharing the header's controls) ----
-    for masked in (False, True):
-        pre = "M" if masked else ""
-        e(f"${pre}DM:")
-        reload()
-        e("and.b32 cnt, w3, 65535;")
-        # tabulated run (MOP_STATIC): one load for the thread-bit members, one for the members outside the tile
-        e(f"and.b32 u, w0, {STATIC};")
-        e("setp.eq.u32 pk, u, 0;")
-        e(f"@pk bra.uni ${pre}DMd;")
-        e("mad.lo.u32 ca, w2, %42, %40;")
-        e("ld.shared.v2.f64 {ar, ai}, [ca];")
-        e(f"mad.lo.u32 p, cnt, {MOP}, p;")
-        e(f"and.b32 u, w0, {PARB};")
-        e("setp.eq.u32 pk, u, 0;")
-        e(f"@pk bra.uni ${pre}DMa;")
-        e("shl.b32 t, w2, 4;")
-        e("add.u32 ca, t, %41;")
-        e("ld.shared.v2.f64 {fr, fi}, [ca];")
-        e("mul.rn.f64 ta, ai, fi;")
-        e("mul.rn.f64 tb, ai, fr;")
-        e("neg.f64 ta, ta;")
-        e("fma.rn.f64 ta, ar, fr, ta;")
-        e("fma.rn.f64 ai, ar, fi, tb;")
-        e("mov.f64 ar, ta;")
-        e(f"bra.uni ${pre}DMa;")
-        e(f"${pre}DMd:")
-        e("mov.f64 ar, 0d3FF0000000000000;")
-        e("mov.f64 ai, 0d0000000000000000;")
-        e(f"${pre}DMl:")
-        e("setp.eq.u32 pq, cnt, 0;")
-        e(f"@pq bra.uni ${pre}DMa;")
-        e("ld.shared.v4.u32 {w0, w1, w2, w3}, [p];")
-        dpar()
-        e(f"and.b32 u, w0, {SKIP0};")
-        e("setp.ne.u32 pk, u, 0;")
-        e("setp.eq.u32 pz, par, 0;")
-        e("and.pred pa, pk, pz;")
-        e(f"@pa bra ${pre}DMn;")
-        e("shl.b32 t, par, 4;")
-        e("add.u32 ca, p, t;")
-        e("ld.shared.v2.f64 {fr, fi}, [ca+16];")
-        e("mul.rn.f64 ta, ai, fi;")            # (ar, ai) *= (fr, fi)
-        e("mul.rn.f64 tb, ai, fr;")
-        e("neg.f64 ta, ta;")
-        e("fma.rn.f64 ta, ar, fr, ta;")
-        e("fma.rn.f64 ai, ar, fi, tb;")
-        e("mov.f64 ar, ta;")
-        e(f"${pre}DMn:")
-        e(f"add.u32 p, p, {MOP};")
-        e("sub.u32 cnt, cnt, 1;")
-        e(f"bra.uni ${pre}DMl;")
-        e(f"${pre}DMa:")
-        e("ld.shared.v4.u32 {h0, h1, h2, h3}, [p];")
-        e("neg.f64 n1, ai;")
+    sect("warm")
+    # One copy of the factor code for every variant; dmv says how the factor is applied at the end:
+    # 0 every slot pattern, 1 under the okmask predicates, 2 + c the patterns with slot bit c set.
+    e("$DM:")
+    e("mov.u32 dmv, 0;")
+    e("bra.uni $DMgo;")
+    for c in range(4):
+        e(f"$DMc{c}:")
+        e(f"and.b32 t, %33, {0xFF << (8 * c)};")
+        e("setp.ne.u32 pk, t, 0;")
+        e("@pk bra $FBDM;")
+        e(f"mov.u32 dmv, {2 + c};")
+        e("bra.uni $DMgo;")
+    e("$FBDM:")
+    e(f"mov.u32 code, {FC_MASKED + FC_DM};")
+    e("bra $MPRE;")
+    e("$MDM:")
+    e("mov.u32 dmv, 1;")
+    e("$DMgo:")
+    reload()
+    e("and.b32 cnt, w3, 65535;")
+    # tabulated run (MOP_STATIC): one load for the thread-bit members, one for the members outside the tile
+    e(f"and.b32 u, w0, {STATIC};")
+    e("setp.eq.u32 pk, u, 0;")
+    e("@pk bra.uni $DMd;")
+    e("mad.lo.u32 ca, w2, %42, %40;")
+    e("ld.shared.v2.f64 {ar, ai}, [ca];")
+    e(f"mad.lo.u32 p, cnt, {MOP}, p;")
+    e(f"and.b32 u, w0, {PARB};")
+    e("setp.eq.u32 pk, u, 0;")
+    e("@pk bra.uni $DMa;")
+    e("shl.b32 t, w2, 4;")
+    e("add.u32 ca, t, %41;")
+    e("ld.shared.v2.f64 {fr, fi}, [ca];")
+    e("mul.rn.f64 ta, ai, fi;")
+    e("mul.rn.f64 tb, ai, fr;")
+    e("neg.f64 ta, ta;")
+    e("fma.rn.f64 ta, ar, fr, ta;")
+    e("fma.rn.f64 ai, ar, fi, tb;")
+    e("mov.f64 ar, ta;")
+    e("bra.uni $DMa;")
+    e("$DMd:")
+    e("mov.f64 ar, 0d3FF0000000000000;")
+    e("mov.f64 ai, 0d0000000000000000;")
+    e("$DMl:")
+    e("setp.eq.u32 pq, cnt, 0;")
+    e("@pq bra.uni $DMa;")
+    e("ld.shared.v4.u32 {w0, w1, w2, w3}, [p];")
+    dpar()
+    e(f"and.b32 u, w0, {SKIP0};")
+    e("setp.ne.u32 pk, u, 0;")
+    e("setp.eq.u32 pz, par, 0;")
+    e("and.pred pa, pk, pz;")
+    e("@pa bra $DMn;")
+    e("shl.b32 t, par, 4;")
+    e("add.u32 ca, p, t;")
+    e("ld.shared.v2.f64 {fr, fi}, [ca+16];")
+    e("mul.rn.f64 ta, ai, fi;")            # (ar, ai) *= (fr, fi)
+    e("mul.rn.f64 tb, ai, fr;")
+    e("neg.f64 ta, ta;")
+    e("fma.rn.f64 ta, ar, fr, ta;")
+    e("fma.rn.f64 ai, ar, fi, tb;")
+    e("mov.f64 ar, ta;")
+    e("$DMn:")
+    e(f"add.u32 p, p, {MOP};")
+    e("sub.u32 cnt, cnt, 1;")
+    e("bra.uni $DMl;")
+    e("$DMa:")
+    e("ld.shared.v2.u32 {h0, h1}, [p];")
+    e("neg.f64 n1, ai;")
+    e("setp.eq.u32 pk, dmv, 0;")
+    e("@pk bra $DMA0;")
+    e("setp.eq.u32 pk, dmv, 1;")
+    e("@pk bra $DMA1;")
+    for c in range(3):
+        e(f"setp.eq.u32 pk, dmv, {2 + c};")
+        e(f"@pk bra $DMAc{c};")
+    for c in (3, 2, 1, 0):
+        e(f"$DMAc{c}:")
         for K in range(NV):
-            g = pred(K, masked)
-            cmul(K, "ar", "ai", "n1", g)
+            if K & (1 << c):
+                cmul(K, "ar", "ai", "n1", "")
         e("bra.uni $TOP;")
+    e("$DMA0:")
+    for K in range(NV):
+        cmul(K, "ar", "ai", "n1", "")
+    e("bra.uni $TOP;")
+    sect("cold")
+    e("$DMA1:")
+    for K in range(NV):
+        g = pred(K, True)
+        cmul(K, "ar", "ai", "n1", g)
+    e("bra.uni $TOP;")
 
     e("$END:")
     e("}")
+    L.extend(SECT["hot"] + SECT["warm"] + SECT["cold"])
 
 
 def main():

@@ -48,6 +48,7 @@ struct PlanCfg {
     int peer_tile_bits = 0;   // tile size of those passes (0 = same as tile_bits): more gathered bits carry more
                               // gates per NVLink exchange
     int force_pinned = -1;    // restore_layout: the local bit a remap pass must trade the global bit with
+    bool single_ctrl = true;  // single-control arms for diagonal forms with one control in a register slot
     uint64_t q_mask() const { return q_num >= 64 ? ~0ull : ((1ull << q_num) - 1ull); }
 };
 
@@ -630,11 +631,32 @@ static int build_plan(const PlanCfg &c, std::vector<POp> &pl, Plan &plan) {
             for (uint32_t k = 0; k < cur.hdr.n_stages; ++k)
                 cur.hdr.stage_end[k] = (uint16_t)(plan.stages[cur.hdr.stage_begin + k].op_end - cur.hdr.op_begin);
             cur.hdr.need_flags = 0;
+            uint32_t member_until = 0;
             for (uint32_t k = 0; k < cur.hdr.n_ops; ++k) {
                 MOp &mk = plan.mops[cur.hdr.op_begin + k];
                 mk.idx = (uint16_t)k;
-                if (!cur.hdr.full && mk.code < (uint8_t)FC_TOTAL)      // control class into the code byte (engine.h)
-                    mk.code = (uint8_t)(mk.code + FC_TOTAL * ((mk.dagger & MOP_CONDB) ? 2 : (mk.dagger & MOP_COND) ? 1 : 0));
+                if (!cur.hdr.full && mk.code < (uint8_t)FC_TOTAL) {
+                    const int cls = (mk.dagger & MOP_CONDB) ? 2 : (mk.dagger & MOP_COND) ? 1 : 0;
+                    // one control, in register slot c: the single-control arm (engine.h FC_DS1 ...); the members
+                    // of a run are data of their header, their codes stay
+                    int c1 = -1;
+                    for (int c = 0; c < TILE_R; ++c) {
+                        uint32_t want = 0;
+                        for (int K = 0; K < TILE_NV; ++K)
+                            if (K & (1 << c)) want |= 1u << K;
+                        if (mk.okmask == want) c1 = c;
+                    }
+                    const uint8_t g = mk.code;
+                    if (cls == 0 && c1 >= 0 && k >= member_until && c.single_ctrl) {
+                        if (g >= (uint8_t)(FC_MASKED + FC_DS) && g < (uint8_t)(FC_MASKED + FC_DS + TILE_R))
+                            mk.code = (uint8_t)(FC_DS1 + 4 * (g - (FC_MASKED + FC_DS)) + c1);
+                        else if (g == (uint8_t)(FC_MASKED + FC_DU)) mk.code = (uint8_t)(FC_DU1 + c1);
+                        else if (g == (uint8_t)(FC_MASKED + FC_DM)) mk.code = (uint8_t)(FC_DM1 + c1);
+                    }
+                    if (g == (uint8_t)FC_DM || g == (uint8_t)(FC_MASKED + FC_DM)) member_until = k + 1u + mk.a_reg;
+                    if (mk.code < (uint8_t)FC_TOTAL)                  // control class into the code byte (engine.h)
+                        mk.code = (uint8_t)(mk.code + FC_TOTAL * cls);
+                }
                 const MBase &mb = plan.bases[cur.hdr.op_begin + k];
                 if (mb.ctrl_base | mb.a_base) cur.hdr.need_flags = 1;
             }
@@ -1049,6 +1071,7 @@ static PlanCfg cfg_of(const qvnt_reg *r) {
     c.remap = r->opt_remap != 0 && r->remap_possible;
     c.peer_chunk_bits = r->opt_peer_chunk_bits;
     c.peer_tile_bits = r->opt_peer_tile_bits;
+    c.single_ctrl = r->knobs.single_ctrl != 0;
     c.ack_cap = r->ack_cap;
     memcpy(c.perm, r->perm, sizeof(c.perm));
     return c;

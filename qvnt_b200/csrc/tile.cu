@@ -589,7 +589,7 @@ __device__ __forceinline__ void stage_ops_fast(const unsigned char *ops, const v
         const unsigned char *const op = p;
         const uint4 h = *reinterpret_cast<const uint4 *>(op);     // w0 | ctrl_thr | a_thr | a_reg + idx << 16
         p += MOP_BYTES;
-        uint32_t code = (h.x & 0xFFu) % (uint32_t)FC_TOTAL;       // (the byte also carries the control class)
+        uint32_t code = fc_generic(h.x & 0xFFu) % (uint32_t)FC_TOTAL;   // (the byte also carries the control class)
         if (h.x & ((uint32_t)MOP_COND << 8)) {
             bool skip = (~vgrp & h.y) != 0u;
             if (h.x & ((uint32_t)MOP_CONDB << 8)) skip = skip || !(flags[h.w >> 16] & 0x80u);
@@ -677,7 +677,8 @@ __device__ __forceinline__ void stage_ops_fast_ptx(const uint32_t ops_s, const u
                                                    amp (&v)[NV], const uint32_t dtab_s, const uint32_t dstride_bytes,
                                                    const uint32_t dout_s) {
     uint32_t vgrp = grp;
-    const uint32_t pb = ops_s + MOP_BYTES * ob, pe = ops_s + MOP_BYTES * oe;
+    const uint32_t pb = ops_s + MOP_BYTES * ob;
+    (void)oe;
     asm volatile(QV_FASTOPS_PTX
                  : "+d"(v[0].x), "+d"(v[0].y), "+d"(v[1].x), "+d"(v[1].y), "+d"(v[2].x), "+d"(v[2].y), "+d"(v[3].x),
                    "+d"(v[3].y), "+d"(v[4].x), "+d"(v[4].y), "+d"(v[5].x), "+d"(v[5].y), "+d"(v[6].x), "+d"(v[6].y),
@@ -685,7 +686,7 @@ __device__ __forceinline__ void stage_ops_fast_ptx(const uint32_t ops_s, const u
                    "+d"(v[10].y), "+d"(v[11].x), "+d"(v[11].y), "+d"(v[12].x), "+d"(v[12].y), "+d"(v[13].x),
                    "+d"(v[13].y), "+d"(v[14].x), "+d"(v[14].y), "+d"(v[15].x), "+d"(v[15].y), "+r"(vgrp), "+r"(inv),
                    "+r"(x.jl), "+r"(x.mine_o), "+l"(x.goff)
-                 : "r"(pb), "r"(pe), "r"(flags_s), "r"(dtab_s), "r"(dout_s), "r"(dstride_bytes)
+                 : "r"(pb), "r"(0u), "r"(flags_s), "r"(dtab_s), "r"(dout_s), "r"(dstride_bytes)
                  : "memory");
 }
 
@@ -729,6 +730,22 @@ constexpr uint32_t META_SLOTS = 3;
 __host__ __device__ inline bool need_flags_smem(const TPassHdr &h, bool full) { return full || h.need_flags != 0u; }      // per-tile op flags rotate through 3 slots: preparing tile i+1 must not
                                         // race with the threads still running the ops of tile i-1
 
+// ---- timeline probe (build variant: make VARIANT=_trace EXTRA=-DQV_TRACE; tools/trace_pass.py) ----
+// Thread 0 of the first QV_TRACE_CTAS CTAs stamps clock64 at the phase boundaries of its first
+// QV_TRACE_TILES tiles; the last local pass and the last remap pass of a run are kept per device.
+#ifdef QV_TRACE
+constexpr int QV_TRACE_CTAS = 16, QV_TRACE_TILES = 48, QV_TRACE_PTS = 8;
+__device__ unsigned long long g_trace[2][QV_TRACE_CTAS][QV_TRACE_TILES][QV_TRACE_PTS];
+__device__ unsigned int g_trace_info[2][8];
+#define QV_STAMP(k)                                                                                        \
+    do {                                                                                                   \
+        if (tid == 0 && (hdr.prefetch & 0x80000000u) && blockIdx.x < QV_TRACE_CTAS && tr_i < QV_TRACE_TILES) \
+            g_trace[hdr.remap ? 1 : 0][blockIdx.x][tr_i][k] = (unsigned long long)clock64();               \
+    } while (0)
+#else
+#define QV_STAMP(k) do { } while (0)
+#endif
+
 template <int THREADS, int MINB, bool FULL, bool BULK, bool PTXOPS, bool DB>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr hdr,
@@ -764,7 +781,10 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     const uint32_t flags_bytes = need_flags_smem(hdr, FULL) ? META_SLOTS * flags_stride : 16u;
     double2 *s_dtab = reinterpret_cast<double2 *>(s_flags_all + flags_bytes);      // 16 * nthr * n_static
     double2 *s_dout = s_dtab + (size_t)nthr * n_static;                            // 16 * META_SLOTS * n_static
-    uint32_t *s_runhdr = reinterpret_cast<uint32_t *>(s_dout + META_SLOTS * n_static);   // 4 * n_static: op index of each run's header
+    uint32_t *s_runhdr = reinterpret_cast<uint32_t *>(s_dout + META_SLOTS * n_static);   // 8 * n_static: position and op index of each run's header
+    // PTX op loop: the code bytes as planned; the copies inside s_ops are rewritten per tile (patch_codes)
+    uint8_t *s_code0 = reinterpret_cast<uint8_t *>(s_runhdr + 2u * n_static);      // n_ops + n_stages
+    constexpr bool PATCH = PTXOPS && !FULL;
 
     const uint32_t shard_shift = segs.shift;
     const uint64_t shard_mask = (1ull << shard_shift) - 1ull;
@@ -805,6 +825,17 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     const uint32_t n_t = T - TR;                     // thread bits per stage
     if (tid < 16u) s_gpos[tid] = hdr.gpos_store[tid];      // where the last stage stores each tile-local bit
     __syncthreads();                                 // the stage descriptors are in shared memory
+    // PTX op loop: ops with controls OUTSIDE the tile (class 2: code >= 2 * FC_TOTAL) are decided once
+    // per tile for all threads, so the loop does not test them: before a tile's first stage the code
+    // byte in shared memory becomes the class 0 / 1 code (controls satisfied) or a skip code.
+    int mine_patch = 0;
+    if (PATCH) {
+        for (uint32_t o = tid; o < n_ops + n_stages; o += nthr) {
+            const uint32_t c0 = s_ops[o].code;
+            s_code0[o] = (uint8_t)c0;
+            mine_patch |= (int)(c0 >= 2u * (uint32_t)FC_TOTAL && c0 < 3u * (uint32_t)FC_TOTAL);
+        }
+    }
     // per-(stage, thread) and per-stage constants, once per kernel
     unsigned long long my_goff = 0;                  // last stage: byte offset of this thread's jl inside the tile's span
     for (uint32_t st = 0; st < n_stages; ++st) {
@@ -824,7 +855,7 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
         for (uint32_t o = 0; o < n_ops + n_stages; ++o) {        // (shared-memory positions: sentinels included)
             const MOp &hd = s_ops[o];
             if (hd.code == (uint8_t)MOP_END) continue;
-            const uint32_t base_code = hd.code % (uint32_t)FC_TOTAL;
+            const uint32_t base_code = fc_generic(hd.code) % (uint32_t)FC_TOTAL;
             if ((base_code != (uint32_t)FC_DM && base_code != (uint32_t)(FC_DM + FC_MASKED)) || !(hd.dagger & MOP_STATIC)) continue;
             double ar = 1.0, ai = 0.0;
             for (uint32_t k = 1; k <= hd.a_reg; ++k) {
@@ -858,12 +889,29 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     // half from.  Handshake per tile: after its load has landed a CTA stores the pass's epoch into
     // the peer's ack word of that tile; before its final stores it waits for its own ack word.  Both
     // GPUs walk the tiles in the same order with the same grid, and a load never waits, so the wait
-    // always ends.
+    // always ends.  Both sides of the handshake are RELAXED system-scope accesses: the ack is sent after
+    // the tile has landed in shared memory (the reads of the peer's copy are over), and the stores it
+    // guards are issued behind a barrier that follows the polling load -- nothing else needs ordering.
+    // (A release store here is a MEMBAR.SYS per tile on thread 0 with the whole CTA waiting at the
+    // stage's barrier: the in-kernel timeline showed ~20k of a remap tile's 44k cycles in it.)
     const bool remap = hdr.remap != 0u;
     const unsigned long long store_keep = remap ? ~(16ull << hdr.remap_b) : ~0ull;
     unsigned int *const ack_mine = segs.ack[segs.rank];
     unsigned int *const ack_peer = remap ? segs.ack[segs.rank ^ (1u << (hdr.remap_g - segs.shift))] : nullptr;
-    __syncthreads();
+    const bool has_patch = __syncthreads_or(mine_patch) != 0;
+    auto patch_codes = [&](const uint32_t slot) {
+        const uint8_t *flags = s_flags_all + slot * flags_stride;
+        for (uint32_t o = tid; o < n_ops + n_stages; o += nthr) {
+            const uint32_t c0 = s_code0[o];
+            if (c0 < 2u * (uint32_t)FC_TOTAL || c0 >= 3u * (uint32_t)FC_TOTAL) continue;
+            MOp &m = s_ops[o];
+            const uint32_t arm = c0 - 2u * (uint32_t)FC_TOTAL;
+            uint32_t c;
+            if (flags[m.idx] & 0x80u) c = arm + (m.ctrl_thr ? (uint32_t)FC_TOTAL : 0u);
+            else c = (arm == (uint32_t)FC_DM || arm == (uint32_t)(FC_DM + FC_MASKED)) ? MOP_NOP_RUN : MOP_NOP;
+            m.code = (uint8_t)c;
+        }
+    };
 
     // Tile counter -> local base index (tile bits and ownership bits clear): the counter's bits
     // are spread over the positions hdr.fixed_mask leaves free.  The CTA's first tile is expanded
@@ -990,29 +1038,43 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
     uint64_t t_cur = blockIdx.x, base_cur = expand(blockIdx.x);
     prepare(t_cur, base_cur, mslot, toff_cur);
     if (t_cur < hdr.n_tiles) issue_load(toff_cur, tile_s);
+#ifdef QV_TRACE
+    uint32_t tr_i = 0;
+    if (tid == 0 && blockIdx.x == 0 && (hdr.prefetch & 0x80000000u)) {
+        unsigned int *inf = g_trace_info[hdr.remap ? 1 : 0];
+        inf[0] = n_stages; inf[1] = n_ops; inf[2] = T; inf[3] = L; inf[4] = nthr; inf[5] = gridDim.x;
+        inf[6] = (unsigned int)hdr.n_tiles; inf[7] = (BULK ? 1u : 0u) | (DB ? 2u : 0u) | (hdr.touches_peer ? 4u : 0u);
+    }
+#endif
     while (t_cur < hdr.n_tiles) {
+        QV_STAMP(0);
         const uint32_t mnext = mslot + 1u == META_SLOTS ? 0u : mslot + 1u;
         uint64_t t_next = t_cur + gridDim.x, base_next = ((base_cur | fixed) + step) & ~fixed;
-        prepare(t_next, base_next, mnext, toff_next);
-        const bool has_next = t_next < hdr.n_tiles;
         if (BULK) {
             mbar_wait(mbar, phase);
             phase ^= 1u;
-            if (need_flags) __syncthreads();           // this tile's flag bytes
+            if (need_flags || DB) __syncthreads();     // this tile's flag bytes; DB: the other buffer is free
         } else {
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             __syncthreads();
-            if (DB && has_next) {
-                // Two buffers: everybody is done with the previous tile (the barrier above), so its
-                // buffer takes the next tile NOW -- a whole tile of compute ahead of its use.
-                issue_load(toff_next, tile_s ^ tile_s0 ^ (tile_s0 + buf_bytes));
-            }
         }
+        QV_STAMP(1);
+        // (the barrier above also says: nobody is still running the previous tile's ops)
+        if (has_patch) patch_codes(mslot);
+        prepare(t_next, base_next, mnext, toff_next);  // need_flags: ends in a barrier when there is a next tile
+        const bool has_next = t_next < hdr.n_tiles;
+        if (has_patch && !has_next) __syncthreads();
+        if (DB && has_next) {
+            // Two buffers: everybody is done with the previous tile (the barrier above), so its
+            // buffer takes the next tile NOW -- a whole tile of compute ahead of its use.
+            issue_load(toff_next, tile_s ^ tile_s0 ^ (tile_s0 + buf_bytes));
+        }
+        QV_STAMP(2);
         const uint8_t *flags = s_flags_all + mslot * flags_stride;
         const uint32_t flags_s = flags_all_s + mslot * flags_stride;
         if (remap && tid == 0)       // "I have read your copy of tile t_cur"
-            asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(ack_peer + t_cur), "r"(hdr.epoch) : "memory");
-        if (hdr.prefetch && has_next) prefetch_tile(toff_next);
+            asm volatile("st.relaxed.sys.global.u32 [%0], %1;\n" ::"l"(ack_peer + t_cur), "r"(hdr.epoch) : "memory");
+        if ((hdr.prefetch & 1u) && has_next) prefetch_tile(toff_next);
 
         for (uint32_t s = 0; s < n_stages; ++s) {
             const bool last = s + 1 == n_stages;
@@ -1030,7 +1092,7 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
                         unsigned int got;
                         unsigned long long spins = 0;
                         do {
-                            asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(got) : "l"(ack_mine + t_cur) : "memory");
+                            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];\n" : "=r"(got) : "l"(ack_mine + t_cur) : "memory");
                             if (got != hdr.epoch && ++spins > (1ull << 24)) {
                                 __nanosleep(1000);
                                 if (spins > (1ull << 24) + 20000000ull) __trap();
@@ -1046,7 +1108,7 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
                     unsigned int got;
                     unsigned long long spins = 0;
                     do {
-                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(got) : "l"(ack_mine + t_cur) : "memory");
+                        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];\n" : "=r"(got) : "l"(ack_mine + t_cur) : "memory");
                         if (got != hdr.epoch && ++spins > (1ull << 24)) {
                             __nanosleep(1000);
                             if (spins > (1ull << 24) + 20000000ull) __trap();      // ~20 s
@@ -1060,6 +1122,7 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
                 // may store before everybody has loaded
                 __syncthreads();
             }
+            if (last) QV_STAMP(5);
             if (active) {
                 uint32_t inv = 0;
                 if (FULL) stage_ops_full(ops_s + MOP_BYTES * s, flags_s, ob, oe, tid, mats, v);
@@ -1070,12 +1133,18 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
                 else
                     stage_ops_fast(reinterpret_cast<const unsigned char *>(s_ops + s), flags, ob, oe, tid, L, x, inv, v,
                                    s_dtab + tid, nthr, s_dout + mslot * n_static);
+                if (last) QV_STAMP(6);
                 if (!last) stage_store_smem(tile_s, x, inv, v);
                 else if (hdr.touches_peer && !remap) stage_store_global(ptr0_s, L, toff_cur, x, inv, v);
                 else stage_store_global_local(shard_base + (toff_cur & store_keep), s_gpos, x, inv, v);
             }
             if (!last) __syncthreads();
+            if (!last && s < 2u) QV_STAMP(3 + s);
         }
+        QV_STAMP(7);
+#ifdef QV_TRACE
+        ++tr_i;
+#endif
         mslot = mnext;
         if (DB) tile_s = tile_s ^ tile_s0 ^ (tile_s0 + buf_bytes);
         t_cur = t_next;
@@ -1096,7 +1165,8 @@ static size_t tile_smem_bytes(const TPassHdr &h, int threads, bool db = false) {
            (flags ? sizeof(MBase) * h.n_ops : 0) + (size_t)32 * h.n_stages + (((size_t)8 << (h.T - h.L)) + 8) +
            (size_t)16 * h.n_stages + (size_t)4 * threads * h.n_stages + 16 +
            (flags ? (size_t)META_SLOTS * ((h.n_ops + 15u) & ~15u) : 16) +
-           (size_t)16 * h.n_static * ((size_t)threads + META_SLOTS) + (size_t)8 * h.n_static;
+           (size_t)16 * h.n_static * ((size_t)threads + META_SLOTS) + (size_t)8 * h.n_static +
+           (((size_t)h.n_ops + h.n_stages + 15u) & ~(size_t)15u);
 }
 
 typedef void (*tile_kernel_t)(const Segs, const TPassHdr, const TStage *, const MOp *, const MBase *, const amp *);
@@ -1110,7 +1180,8 @@ static tile_kernel_t pick_kernel(bool full, bool bulk, bool ptx) {
 
 static tile_kernel_t select_kernel(int threads, int ctas, bool full, bool bulk, bool ptx, bool db) {
     // two tile buffers: the cp.async fast path with the PTX op loop, 3 CTAs of 128 threads per SM
-    if (db && threads == 128 && !full && !bulk && ptx) return k_tile_pass<128, 3, false, false, true, true>;
+    if (db && threads == 128 && !full && ptx)
+        return bulk ? k_tile_pass<128, 3, false, true, true, true> : k_tile_pass<128, 3, false, false, true, true>;
     if (threads == 256) return pick_kernel<256, 2>(full, bulk, ptx);
     if (ctas == 4) return pick_kernel<128, 4>(full, bulk, ptx);
     if (ctas == 5 && !full && !bulk && ptx) return k_tile_pass<128, 5, false, false, true, false>;
@@ -1156,8 +1227,8 @@ int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, con
     // Two tile buffers (the next tile is loaded a whole tile of compute ahead): measured no gain, for
     // local and for peer passes alike -- the exposed wait is not the load's latency -- so only on request.
     const bool bulk = knobs.bulk > 0 || (knobs.bulk < 0 && hdr.touches_peer);
-    const bool want_db = knobs.double_buffer > 0;
-    bool db = want_db && threads == 128 && hdr.T == 11 && !hdr.full && !bulk && knobs.ptx_ops &&
+    const bool want_db = knobs.double_buffer == 1 || (knobs.double_buffer == 2 && hdr.touches_peer);
+    bool db = want_db && threads == 128 && hdr.T == 11 && !hdr.full && knobs.ptx_ops &&
               2 * (tile_smem_bytes(hdr, threads, true) + 1024) <= TILE_SMEM_MAX;
     const tile_kernel_t kern = select_kernel(threads == 256 ? 256 : 128, knobs.ctas_per_sm, hdr.full != 0, bulk,
                                              knobs.ptx_ops != 0, db);
@@ -1170,8 +1241,33 @@ int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, con
     if (grid > hdr.n_tiles) grid = hdr.n_tiles;
     TPassHdr h2 = hdr;
     h2.prefetch = knobs.prefetch ? 1u : 0u;
+#ifdef QV_TRACE
+    {   // the probe keeps the pass with the most ops of each kind (local / remap)
+        static uint32_t best[2] = {0u, 0u};
+        const int kind = hdr.remap ? 1 : 0;
+        if (hdr.n_ops >= best[kind]) {
+            best[kind] = hdr.n_ops;
+            h2.prefetch |= 0x80000000u;
+        }
+    }
+#endif
     kern<<<(unsigned)grid, threads, smem, st>>>(segs, h2, d_stages, d_ops, d_bases, mat_table);
     return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 
 }  // namespace qv
+
+#ifdef QV_TRACE
+// debug builds only: copies device `dev`'s probe (kind 0: last local pass, 1: last remap pass) to the host
+extern "C" int qvnt_debug_trace(int dev, int kind, unsigned long long *stamps, unsigned int *info) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(dev);
+    cudaDeviceSynchronize();
+    const size_t n = sizeof(unsigned long long) * qv::QV_TRACE_CTAS * qv::QV_TRACE_TILES * qv::QV_TRACE_PTS;
+    cudaError_t e = cudaMemcpyFromSymbol(stamps, qv::g_trace, n, n * (size_t)kind);
+    if (e == cudaSuccess) e = cudaMemcpyFromSymbol(info, qv::g_trace_info, 32, 32 * (size_t)kind);
+    cudaSetDevice(cur);
+    return e == cudaSuccess ? 0 : -1;
+}
+#endif

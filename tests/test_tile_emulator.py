@@ -46,8 +46,9 @@ def _emulate(oracle, n, circ, psi, world=1, **kw):
             qa, qb = perm.index(p0.rg), perm.index(p0.rb)
             perm[qa], perm[qb] = p0.rb, p0.rg
         for st in p0.stages:
-            n_lazy += sum(1 for m in st.mops if m.code % emu.FC_TOTAL in (emu.FC_LX, emu.FC_LI))
-            n_runs += sum(1 for m in st.mops if m.code % emu.FC_TOTAL in (emu.FC_DM, emu.FC_DM + emu.FC_MASKED))
+            gen = [emu.generic_code(m) % emu.FC_TOTAL for m in st.mops]     # (single-control arms -> their generic code)
+            n_lazy += sum(1 for c in gen if c in (emu.FC_LX, emu.FC_LI))
+            n_runs += sum(1 for c in gen if c in (emu.FC_DM, emu.FC_DM + emu.FC_MASKED))
     _emulate.last_remaps = n_remap
     return emu.to_logical(psi, perm), n_fast, n_lazy, n_runs
 

@@ -19,6 +19,28 @@ FC_PR, FC_PX, FC_DS, FC_DU, FC_DG, FC_LX, FC_LI, FC_DM, FC_MASKED, FC_SW = 0, 4,
 FC_TOTAL = 38
 MOP_SKIP0, MOP_COND, MOP_PARB, MOP_CONDB, MOP_ATHR, MOP_STATIC = 0x02, 0x04, 0x08, 0x10, 0x20, 0x40
 NV = 16
+FC_DS1, FC_DU1, FC_DM1, FC_SPECIAL_END = 114, 130, 134, 138
+
+
+def generic_code(m) -> int:
+    """The single-control arms (engine.h FC_DS1 / FC_DU1 / FC_DM1: one control in register slot c, no
+    other control) compute what the generic masked arm computes under okmask = 'slot bit c set'."""
+    c = m.code
+    if not (FC_DS1 <= c < FC_SPECIAL_END):
+        return c
+    assert not (m.flags & (MOP_COND | MOP_CONDB)) and m.ctrl_thr == 0 and m.ctrl_base == 0
+    if c < FC_DU1:
+        j, ctl = (c - FC_DS1) >> 2, (c - FC_DS1) & 3
+        assert j != ctl
+        g = FC_MASKED + FC_DS + j
+    elif c < FC_DM1:
+        ctl = c - FC_DU1
+        g = FC_MASKED + FC_DU
+    else:
+        ctl = c - FC_DM1
+        g = FC_MASKED + FC_DM
+    assert m.okmask == sum(1 << K for K in range(NV) if K & (1 << ctl)), "single-control arm with another okmask"
+    return g
 U64 = (1 << 64) - 1
 
 
@@ -86,8 +108,9 @@ def run_stage(tile: np.ndarray, st, T: int, gbase: int):
 
     while i < len(mops):
         m = mops[i]
-        code = m.code % FC_TOTAL                 # the byte also carries the control class (engine.h)
-        assert m.code // FC_TOTAL == (2 if m.flags & MOP_CONDB else 1 if m.flags & MOP_COND else 0)
+        raw = generic_code(m)
+        code = raw % FC_TOTAL                    # the byte also carries the control class (engine.h)
+        assert raw // FC_TOTAL == (2 if m.flags & MOP_CONDB else 1 if m.flags & MOP_COND else 0)
         masked = False
         if FC_MASKED <= code < FC_SW:
             code -= FC_MASKED
@@ -101,14 +124,15 @@ def run_stage(tile: np.ndarray, st, T: int, gbase: int):
             if m.flags & MOP_STATIC:
                 # tabulated run: the kernel takes the thread-bit members' factor from a table built with
                 # vgrp == thread index, and the outside members' factor from a per-tile table
-                assert not any(q.code % FC_TOTAL == FC_LX for q in mops), "a tabulated run needs vgrp == thread index"
+                assert not any(q.code < 3 * FC_TOTAL and q.code % FC_TOTAL == FC_LX for q in mops), \
+                    "a tabulated run needs vgrp == thread index"
                 assert all((e.a_thr != 0) != (e.a_base != 0) for e in mops[i + 1:i + 1 + cnt])
                 assert bool(m.flags & MOP_PARB) == any(e.a_base != 0 for e in mops[i + 1:i + 1 + cnt])
                 assert 0 <= m.a_thr < 12
             acc = np.ones(G, dtype=np.complex128)
             for k in range(1, cnt + 1):
                 e = mops[i + k]
-                assert e.code % FC_TOTAL in (FC_DU, FC_MASKED + FC_DU) and e.okmask == m.okmask and e.ctrl_thr == m.ctrl_thr \
+                assert e.code < 3 * FC_TOTAL and e.code % FC_TOTAL in (FC_DU, FC_MASKED + FC_DU) and e.okmask == m.okmask and e.ctrl_thr == m.ctrl_thr \
                     and e.ctrl_base == m.ctrl_base
                 par = dpar(e)
                 f = np.where(par == 1, complex(e.c[2], e.c[3]), complex(e.c[0], e.c[1]))

@@ -47,7 +47,13 @@ def main():
                     cnt["diag_run_member"] += 1
                     skip -= 1
                     continue
-                c = m.code % 38
+                raw = m.code
+                if 114 <= raw < 138:          # single-control arms (engine.h FC_DS1 / FC_DU1 / FC_DM1)
+                    cnt["single-control " + ("diag_slot" if raw < 130 else "diag_thread" if raw < 134 else "diag_run_header")] += 1
+                    if raw >= 134:
+                        skip = m.a_reg
+                    continue
+                c = raw % 38
                 c = c - 17 if 17 <= c < 34 else c
                 base = max(k for k in NAMES if k <= c)
                 cnt[NAMES[base]] += 1
