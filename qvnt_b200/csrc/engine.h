@@ -207,7 +207,7 @@ struct TPassHdr {
     uint32_t need_flags;         // some op of the pass depends on index bits outside the tile (per-tile flag bytes)
     uint32_t n_static;           // tabulated diagonal runs (MOP_STATIC headers) of the pass
     uint32_t prefetch;           // filled by launch_tile_pass (TileKnobs): L2 prefetch of the next tile's chunks
-    uint32_t _pad4;
+    uint32_t uses_sc;            // some op of the pass has a single-control code (FC_DS1 ...): the kernel flavour with those arms
     uint64_t fixed_mask;         // local index bits the tile counter does NOT enumerate (tile bits + ownership bits)
     uint16_t stage_end[TILE_MAX_STAGES];   // ops of stage s: [stage_end[s-1], stage_end[s]) relative to op_begin
     Fixed fx;                    // the same enumeration bit by bit (host side: describe / tests)

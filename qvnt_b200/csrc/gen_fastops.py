@@ -38,7 +38,6 @@ MOP = 80
 # Code layout: the arms a random circuit keeps jumping between (pairs, unmasked diagonals, lazy x, the
 # controlled swaps) are emitted first and stay together behind the prologue (the SM's instruction
 # cache holds 32 KB); then the arms of qft-like circuits; the generic predicated arms come last.
-L = []
 SECT = {"hot": [], "warm": [], "cold": []}
 CUR = ["hot"]
 
@@ -129,7 +128,11 @@ def dpar():
     e("and.b32 par, par, 1;")
 
 
-def gen():
+def gen(sc):
+    """sc: with the single-control arms (FC_DS1 / FC_DU1 / FC_DM1).  The kernel is compiled in both
+    flavours (tile.cu, template parameter SC) and a pass without such ops runs the lean one: the arms are
+    never executed there, but one asm block is ONE register-allocation problem for ptxas, and with them
+    in it the arms of a random circuit came out 3 % slower (A/B on one box, profiles/r02s_ab.txt)."""
     arm = ["$TOP"] * FC_TOTAL            # the arms proper
     for j in range(4):
         arm[FC_PR + j] = f"$PR{j}"
@@ -155,9 +158,9 @@ def gen():
     for c in range(4):
         for j in range(4):
             if j != c:
-                tbl[FC_DS1 + 4 * j + c] = f"$DS{j}c{c}"
-        tbl[FC_DU1 + c] = f"$DUc{c}"
-        tbl[FC_DM1 + c] = f"$DMc{c}"
+                tbl[FC_DS1 + 4 * j + c] = f"$DS{j}c{c}" if sc else "$BAD"
+        tbl[FC_DU1 + c] = f"$DUc{c}" if sc else "$BAD"
+        tbl[FC_DM1 + c] = f"$DMc{c}" if sc else "$BAD"
     tbl[253] = "$SKIPRUN"                # engine.h MOP_NOP_RUN: a switched-off run header takes its members with it
     tbl[254] = "$TOP"                    # engine.h MOP_NOP: an op this tile's outside controls switch off
     tbl[255] = "$END"                    # the sentinel descriptor behind every stage (engine.h MOP_END)
@@ -168,7 +171,7 @@ def gen():
 
     e("{")
     e(".reg .pred pq, pb, pk, pz, pa;")
-    e(".reg .u32 p, w0, w1, w2, w3, h0, h1, code, t, u, blk, ca, ok, fl, cnt, par, lo, hi, areg, ib, dmv;")
+    e(".reg .u32 p, w0, w1, w2, w3, h0, h1, code, t, u, blk, ca, ok, fl, cnt, par, lo, hi, areg, ib" + (", dmv" if sc else "") + ";")
     e(".reg .f64 c0, c1, c2, c3, ta, tb, tc, td, n1, n2, ar, ai, fr, fi;")
     e(".reg .u64 g64;")
     e("$TBL: .branchtargets " + ", ".join(tbl) + ";")
@@ -321,7 +324,7 @@ def gen():
         for j in range(4):
             ds_arm(("M" if masked else "") + f"DS{j}", j, masked)
     sect("warm")
-    for j in range(4):
+    for j in range(4 if sc else 0):
         for c in range(4):
             if c != j:
                 ds_arm(f"DS{j}c{c}", j, False, only=c)
@@ -360,11 +363,12 @@ def gen():
     sect("cold")
     du_arm("MDU", True)
     sect("warm")
-    for c in range(4):
+    for c in range(4 if sc else 0):
         du_arm(f"DUc{c}", False, only=c)
-    e("$FBDU:")
-    e(f"mov.u32 code, {FC_MASKED + FC_DU};")
-    e("bra $MPRE;")
+    if sc:
+        e("$FBDU:")
+        e(f"mov.u32 code, {FC_MASKED + FC_DU};")
+        e("bra $MPRE;")
 
     # ---- diagonal, any set of target bits in register slots (always dispatched as masked) ----
     sect("cold")
@@ -425,115 +429,186 @@ def gen():
     e("bra.uni $TOP;")
 
     # ---- merged diagonal run: header + cnt members (FC_DU forms sharing the header's controls) ----
-    sect("warm")
-    # One copy of the factor code for every variant; dmv says how the factor is applied at the end:
-    # 0 every slot pattern, 1 under the okmask predicates, 2 + c the patterns with slot bit c set.
-    e("$DM:")
-    e("mov.u32 dmv, 0;")
-    e("bra.uni $DMgo;")
-    for c in range(4):
-        e(f"$DMc{c}:")
-        e(f"and.b32 t, %33, {0xFF << (8 * c)};")
-        e("setp.ne.u32 pk, t, 0;")
-        e("@pk bra $FBDM;")
-        e(f"mov.u32 dmv, {2 + c};")
+    if not sc:
+        # lean flavour: one copy per arm, no variant register
+        for masked in (False, True):
+            pre = "M" if masked else ""
+            sect("cold" if masked else "warm")
+            e(f"${pre}DM:")
+            reload()
+            e("and.b32 cnt, w3, 65535;")
+            # tabulated run (MOP_STATIC): one load for the thread-bit members, one for the members outside the tile
+            e(f"and.b32 u, w0, {STATIC};")
+            e("setp.eq.u32 pk, u, 0;")
+            e(f"@pk bra.uni ${pre}DMd;")
+            e("mad.lo.u32 ca, w2, %42, %40;")
+            e("ld.shared.v2.f64 {ar, ai}, [ca];")
+            e(f"mad.lo.u32 p, cnt, {MOP}, p;")
+            e(f"and.b32 u, w0, {PARB};")
+            e("setp.eq.u32 pk, u, 0;")
+            e(f"@pk bra.uni ${pre}DMa;")
+            e("shl.b32 t, w2, 4;")
+            e("add.u32 ca, t, %41;")
+            e("ld.shared.v2.f64 {fr, fi}, [ca];")
+            e("mul.rn.f64 ta, ai, fi;")
+            e("mul.rn.f64 tb, ai, fr;")
+            e("neg.f64 ta, ta;")
+            e("fma.rn.f64 ta, ar, fr, ta;")
+            e("fma.rn.f64 ai, ar, fi, tb;")
+            e("mov.f64 ar, ta;")
+            e(f"bra.uni ${pre}DMa;")
+            e(f"${pre}DMd:")
+            e("mov.f64 ar, 0d3FF0000000000000;")
+            e("mov.f64 ai, 0d0000000000000000;")
+            e(f"${pre}DMl:")
+            e("setp.eq.u32 pq, cnt, 0;")
+            e(f"@pq bra.uni ${pre}DMa;")
+            e("ld.shared.v4.u32 {w0, w1, w2, w3}, [p];")
+            dpar()
+            e(f"and.b32 u, w0, {SKIP0};")
+            e("setp.ne.u32 pk, u, 0;")
+            e("setp.eq.u32 pz, par, 0;")
+            e("and.pred pa, pk, pz;")
+            e(f"@pa bra ${pre}DMn;")
+            e("shl.b32 t, par, 4;")
+            e("add.u32 ca, p, t;")
+            e("ld.shared.v2.f64 {fr, fi}, [ca+16];")
+            e("mul.rn.f64 ta, ai, fi;")            # (ar, ai) *= (fr, fi)
+            e("mul.rn.f64 tb, ai, fr;")
+            e("neg.f64 ta, ta;")
+            e("fma.rn.f64 ta, ar, fr, ta;")
+            e("fma.rn.f64 ai, ar, fi, tb;")
+            e("mov.f64 ar, ta;")
+            e(f"${pre}DMn:")
+            e(f"add.u32 p, p, {MOP};")
+            e("sub.u32 cnt, cnt, 1;")
+            e(f"bra.uni ${pre}DMl;")
+            e(f"${pre}DMa:")
+            e("ld.shared.v2.u32 {h0, h1}, [p];")
+            e("neg.f64 n1, ai;")
+            for K in range(NV):
+                g = pred(K, masked)
+                cmul(K, "ar", "ai", "n1", g)
+            e("bra.uni $TOP;")
+    else:
+        sect("warm")
+        # One copy of the factor code for every variant; dmv says how the factor is applied at the end:
+        # 0 every slot pattern, 1 under the okmask predicates, 2 + c the patterns with slot bit c set.
+        e("$DM:")
+        e("mov.u32 dmv, 0;")
         e("bra.uni $DMgo;")
-    e("$FBDM:")
-    e(f"mov.u32 code, {FC_MASKED + FC_DM};")
-    e("bra $MPRE;")
-    e("$MDM:")
-    e("mov.u32 dmv, 1;")
-    e("$DMgo:")
-    reload()
-    e("and.b32 cnt, w3, 65535;")
-    # tabulated run (MOP_STATIC): one load for the thread-bit members, one for the members outside the tile
-    e(f"and.b32 u, w0, {STATIC};")
-    e("setp.eq.u32 pk, u, 0;")
-    e("@pk bra.uni $DMd;")
-    e("mad.lo.u32 ca, w2, %42, %40;")
-    e("ld.shared.v2.f64 {ar, ai}, [ca];")
-    e(f"mad.lo.u32 p, cnt, {MOP}, p;")
-    e(f"and.b32 u, w0, {PARB};")
-    e("setp.eq.u32 pk, u, 0;")
-    e("@pk bra.uni $DMa;")
-    e("shl.b32 t, w2, 4;")
-    e("add.u32 ca, t, %41;")
-    e("ld.shared.v2.f64 {fr, fi}, [ca];")
-    e("mul.rn.f64 ta, ai, fi;")
-    e("mul.rn.f64 tb, ai, fr;")
-    e("neg.f64 ta, ta;")
-    e("fma.rn.f64 ta, ar, fr, ta;")
-    e("fma.rn.f64 ai, ar, fi, tb;")
-    e("mov.f64 ar, ta;")
-    e("bra.uni $DMa;")
-    e("$DMd:")
-    e("mov.f64 ar, 0d3FF0000000000000;")
-    e("mov.f64 ai, 0d0000000000000000;")
-    e("$DMl:")
-    e("setp.eq.u32 pq, cnt, 0;")
-    e("@pq bra.uni $DMa;")
-    e("ld.shared.v4.u32 {w0, w1, w2, w3}, [p];")
-    dpar()
-    e(f"and.b32 u, w0, {SKIP0};")
-    e("setp.ne.u32 pk, u, 0;")
-    e("setp.eq.u32 pz, par, 0;")
-    e("and.pred pa, pk, pz;")
-    e("@pa bra $DMn;")
-    e("shl.b32 t, par, 4;")
-    e("add.u32 ca, p, t;")
-    e("ld.shared.v2.f64 {fr, fi}, [ca+16];")
-    e("mul.rn.f64 ta, ai, fi;")            # (ar, ai) *= (fr, fi)
-    e("mul.rn.f64 tb, ai, fr;")
-    e("neg.f64 ta, ta;")
-    e("fma.rn.f64 ta, ar, fr, ta;")
-    e("fma.rn.f64 ai, ar, fi, tb;")
-    e("mov.f64 ar, ta;")
-    e("$DMn:")
-    e(f"add.u32 p, p, {MOP};")
-    e("sub.u32 cnt, cnt, 1;")
-    e("bra.uni $DMl;")
-    e("$DMa:")
-    e("ld.shared.v2.u32 {h0, h1}, [p];")
-    e("neg.f64 n1, ai;")
-    e("setp.eq.u32 pk, dmv, 0;")
-    e("@pk bra $DMA0;")
-    e("setp.eq.u32 pk, dmv, 1;")
-    e("@pk bra $DMA1;")
-    for c in range(3):
-        e(f"setp.eq.u32 pk, dmv, {2 + c};")
-        e(f"@pk bra $DMAc{c};")
-    for c in (3, 2, 1, 0):
-        e(f"$DMAc{c}:")
+        for c in range(4):
+            e(f"$DMc{c}:")
+            e(f"and.b32 t, %33, {0xFF << (8 * c)};")
+            e("setp.ne.u32 pk, t, 0;")
+            e("@pk bra $FBDM;")
+            e(f"mov.u32 dmv, {2 + c};")
+            e("bra.uni $DMgo;")
+        e("$FBDM:")
+        e(f"mov.u32 code, {FC_MASKED + FC_DM};")
+        e("bra $MPRE;")
+        e("$MDM:")
+        e("mov.u32 dmv, 1;")
+        e("$DMgo:")
+        reload()
+        e("and.b32 cnt, w3, 65535;")
+        # tabulated run (MOP_STATIC): one load for the thread-bit members, one for the members outside the tile
+        e(f"and.b32 u, w0, {STATIC};")
+        e("setp.eq.u32 pk, u, 0;")
+        e("@pk bra.uni $DMd;")
+        e("mad.lo.u32 ca, w2, %42, %40;")
+        e("ld.shared.v2.f64 {ar, ai}, [ca];")
+        e(f"mad.lo.u32 p, cnt, {MOP}, p;")
+        e(f"and.b32 u, w0, {PARB};")
+        e("setp.eq.u32 pk, u, 0;")
+        e("@pk bra.uni $DMa;")
+        e("shl.b32 t, w2, 4;")
+        e("add.u32 ca, t, %41;")
+        e("ld.shared.v2.f64 {fr, fi}, [ca];")
+        e("mul.rn.f64 ta, ai, fi;")
+        e("mul.rn.f64 tb, ai, fr;")
+        e("neg.f64 ta, ta;")
+        e("fma.rn.f64 ta, ar, fr, ta;")
+        e("fma.rn.f64 ai, ar, fi, tb;")
+        e("mov.f64 ar, ta;")
+        e("bra.uni $DMa;")
+        e("$DMd:")
+        e("mov.f64 ar, 0d3FF0000000000000;")
+        e("mov.f64 ai, 0d0000000000000000;")
+        e("$DMl:")
+        e("setp.eq.u32 pq, cnt, 0;")
+        e("@pq bra.uni $DMa;")
+        e("ld.shared.v4.u32 {w0, w1, w2, w3}, [p];")
+        dpar()
+        e(f"and.b32 u, w0, {SKIP0};")
+        e("setp.ne.u32 pk, u, 0;")
+        e("setp.eq.u32 pz, par, 0;")
+        e("and.pred pa, pk, pz;")
+        e("@pa bra $DMn;")
+        e("shl.b32 t, par, 4;")
+        e("add.u32 ca, p, t;")
+        e("ld.shared.v2.f64 {fr, fi}, [ca+16];")
+        e("mul.rn.f64 ta, ai, fi;")            # (ar, ai) *= (fr, fi)
+        e("mul.rn.f64 tb, ai, fr;")
+        e("neg.f64 ta, ta;")
+        e("fma.rn.f64 ta, ar, fr, ta;")
+        e("fma.rn.f64 ai, ar, fi, tb;")
+        e("mov.f64 ar, ta;")
+        e("$DMn:")
+        e(f"add.u32 p, p, {MOP};")
+        e("sub.u32 cnt, cnt, 1;")
+        e("bra.uni $DMl;")
+        e("$DMa:")
+        e("ld.shared.v2.u32 {h0, h1}, [p];")
+        e("neg.f64 n1, ai;")
+        e("setp.eq.u32 pk, dmv, 0;")
+        e("@pk bra $DMA0;")
+        e("setp.eq.u32 pk, dmv, 1;")
+        e("@pk bra $DMA1;")
+        for c in range(3):
+            e(f"setp.eq.u32 pk, dmv, {2 + c};")
+            e(f"@pk bra $DMAc{c};")
+        for c in (3, 2, 1, 0):
+            e(f"$DMAc{c}:")
+            for K in range(NV):
+                if K & (1 << c):
+                    cmul(K, "ar", "ai", "n1", "")
+            e("bra.uni $TOP;")
+        e("$DMA0:")
         for K in range(NV):
-            if K & (1 << c):
-                cmul(K, "ar", "ai", "n1", "")
+            cmul(K, "ar", "ai", "n1", "")
         e("bra.uni $TOP;")
-    e("$DMA0:")
-    for K in range(NV):
-        cmul(K, "ar", "ai", "n1", "")
-    e("bra.uni $TOP;")
-    sect("cold")
-    e("$DMA1:")
-    for K in range(NV):
-        g = pred(K, True)
-        cmul(K, "ar", "ai", "n1", g)
-    e("bra.uni $TOP;")
+        sect("cold")
+        e("$DMA1:")
+        for K in range(NV):
+            g = pred(K, True)
+            cmul(K, "ar", "ai", "n1", g)
+        e("bra.uni $TOP;")
 
+    sect("cold")
+    if not sc:
+        e("$BAD:")                  # a single-control code in the lean flavour: a launch-selection bug, fail loudly
+        e("trap;")
     e("$END:")
     e("}")
-    L.extend(SECT["hot"] + SECT["warm"] + SECT["cold"])
+    out = SECT["hot"] + SECT["warm"] + SECT["cold"]
+    for k in SECT:
+        SECT[k] = []
+    CUR[0] = "hot"
+    return out
 
 
 def main():
-    gen()
     out = sys.argv[1] if len(sys.argv) > 1 else "fastops_ptx.inc"
     with open(out, "w") as f:
         f.write("// GENERATED by gen_fastops.py -- do not edit; the op loop of the FAST stage interpreter.\n")
-        f.write("#define QV_FASTOPS_PTX \\\n")
-        for i, s in enumerate(L):
-            s = s.replace("$", "QF_")
-            f.write(f'    "{s}\\n\\t"' + (" \\\n" if i + 1 < len(L) else "\n"))
-    print(f"{out}: {len(L)} PTX lines")
+        for name, sc in (("QV_FASTOPS_PTX", False), ("QV_FASTOPS_PTX_SC", True)):
+            lines = gen(sc)
+            f.write(f"#define {name} \\\n")
+            for i, s in enumerate(lines):
+                s = s.replace("$", "QF_")
+                f.write(f'    "{s}\\n\\t"' + (" \\\n" if i + 1 < len(lines) else "\n"))
+            print(f"{out}: {name} {len(lines)} PTX lines")
 
 
 if __name__ == "__main__":

@@ -631,6 +631,7 @@ static int build_plan(const PlanCfg &c, std::vector<POp> &pl, Plan &plan) {
             for (uint32_t k = 0; k < cur.hdr.n_stages; ++k)
                 cur.hdr.stage_end[k] = (uint16_t)(plan.stages[cur.hdr.stage_begin + k].op_end - cur.hdr.op_begin);
             cur.hdr.need_flags = 0;
+            cur.hdr.uses_sc = 0;
             uint32_t member_until = 0;
             for (uint32_t k = 0; k < cur.hdr.n_ops; ++k) {
                 MOp &mk = plan.mops[cur.hdr.op_begin + k];
@@ -656,6 +657,7 @@ static int build_plan(const PlanCfg &c, std::vector<POp> &pl, Plan &plan) {
                     if (g == (uint8_t)FC_DM || g == (uint8_t)(FC_MASKED + FC_DM)) member_until = k + 1u + mk.a_reg;
                     if (mk.code < (uint8_t)FC_TOTAL)                  // control class into the code byte (engine.h)
                         mk.code = (uint8_t)(mk.code + FC_TOTAL * cls);
+                    else cur.hdr.uses_sc = 1;
                 }
                 const MBase &mb = plan.bases[cur.hdr.op_begin + k];
                 if (mb.ctrl_base | mb.a_base) cur.hdr.need_flags = 1;

@@ -672,6 +672,7 @@ __device__ __forceinline__ void stage_ops_fast(const unsigned char *ops, const v
 // compare tree plus divergence bookkeeping (~40 instructions and several dependent branches per op);
 // this one spends ~20.  Option "ptx_ops" (default 1) selects it; the C++ loop stays as the readable
 // specification and the A/B baseline.
+template <bool SC>
 __device__ __forceinline__ void stage_ops_fast_ptx(const uint32_t ops_s, const uint32_t flags_s, const uint32_t ob,
                                                    const uint32_t oe, const uint32_t grp, StageCtx &x, uint32_t &inv,
                                                    amp (&v)[NV], const uint32_t dtab_s, const uint32_t dstride_bytes,
@@ -679,15 +680,19 @@ __device__ __forceinline__ void stage_ops_fast_ptx(const uint32_t ops_s, const u
     uint32_t vgrp = grp;
     const uint32_t pb = ops_s + MOP_BYTES * ob;
     (void)oe;
-    asm volatile(QV_FASTOPS_PTX
-                 : "+d"(v[0].x), "+d"(v[0].y), "+d"(v[1].x), "+d"(v[1].y), "+d"(v[2].x), "+d"(v[2].y), "+d"(v[3].x),
-                   "+d"(v[3].y), "+d"(v[4].x), "+d"(v[4].y), "+d"(v[5].x), "+d"(v[5].y), "+d"(v[6].x), "+d"(v[6].y),
-                   "+d"(v[7].x), "+d"(v[7].y), "+d"(v[8].x), "+d"(v[8].y), "+d"(v[9].x), "+d"(v[9].y), "+d"(v[10].x),
-                   "+d"(v[10].y), "+d"(v[11].x), "+d"(v[11].y), "+d"(v[12].x), "+d"(v[12].y), "+d"(v[13].x),
-                   "+d"(v[13].y), "+d"(v[14].x), "+d"(v[14].y), "+d"(v[15].x), "+d"(v[15].y), "+r"(vgrp), "+r"(inv),
-                   "+r"(x.jl), "+r"(x.mine_o), "+l"(x.goff)
-                 : "r"(pb), "r"(0u), "r"(flags_s), "r"(dtab_s), "r"(dout_s), "r"(dstride_bytes)
-                 : "memory");
+    // SC: the flavour with the single-control arms (gen_fastops.py explains why there are two)
+#define QV_FASTOPS_OPERANDS                                                                                          \
+                 : "+d"(v[0].x), "+d"(v[0].y), "+d"(v[1].x), "+d"(v[1].y), "+d"(v[2].x), "+d"(v[2].y), "+d"(v[3].x), \
+                   "+d"(v[3].y), "+d"(v[4].x), "+d"(v[4].y), "+d"(v[5].x), "+d"(v[5].y), "+d"(v[6].x), "+d"(v[6].y), \
+                   "+d"(v[7].x), "+d"(v[7].y), "+d"(v[8].x), "+d"(v[8].y), "+d"(v[9].x), "+d"(v[9].y), "+d"(v[10].x),\
+                   "+d"(v[10].y), "+d"(v[11].x), "+d"(v[11].y), "+d"(v[12].x), "+d"(v[12].y), "+d"(v[13].x),         \
+                   "+d"(v[13].y), "+d"(v[14].x), "+d"(v[14].y), "+d"(v[15].x), "+d"(v[15].y), "+r"(vgrp), "+r"(inv), \
+                   "+r"(x.jl), "+r"(x.mine_o), "+l"(x.goff)                                                          \
+                 : "r"(pb), "r"(0u), "r"(flags_s), "r"(dtab_s), "r"(dout_s), "r"(dstride_bytes)                      \
+                 : "memory"
+    if (SC) asm volatile(QV_FASTOPS_PTX_SC QV_FASTOPS_OPERANDS);
+    else asm volatile(QV_FASTOPS_PTX QV_FASTOPS_OPERANDS);
+#undef QV_FASTOPS_OPERANDS
 }
 
 // ---- TMA bulk copy + mbarrier (tile loads) -------------------------------------------------------
@@ -746,7 +751,7 @@ __device__ unsigned int g_trace_info[2][8];
 #define QV_STAMP(k) do { } while (0)
 #endif
 
-template <int THREADS, int MINB, bool FULL, bool BULK, bool PTXOPS, bool DB>
+template <int THREADS, int MINB, bool FULL, bool BULK, bool PTXOPS, bool DB, bool SC = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr hdr,
             const TStage *__restrict__ g_stages, const MOp *__restrict__ g_ops,
@@ -1127,7 +1132,7 @@ k_tile_pass(const __grid_constant__ Segs segs, const __grid_constant__ TPassHdr 
                 uint32_t inv = 0;
                 if (FULL) stage_ops_full(ops_s + MOP_BYTES * s, flags_s, ob, oe, tid, mats, v);
                 else if (PTXOPS)
-                    stage_ops_fast_ptx(ops_s + MOP_BYTES * s, flags_s, ob, oe, tid, x, inv, v,
+                    stage_ops_fast_ptx<SC>(ops_s + MOP_BYTES * s, flags_s, ob, oe, tid, x, inv, v,
                                        (uint32_t)__cvta_generic_to_shared(s_dtab + tid), 16u * nthr,
                                        (uint32_t)__cvta_generic_to_shared(s_dout + mslot * n_static));
                 else
@@ -1178,8 +1183,15 @@ static tile_kernel_t pick_kernel(bool full, bool bulk, bool ptx) {
     return bulk ? k_tile_pass<THREADS, MINB, false, true, false, false> : k_tile_pass<THREADS, MINB, false, false, false, false>;
 }
 
-static tile_kernel_t select_kernel(int threads, int ctas, bool full, bool bulk, bool ptx, bool db) {
-    // two tile buffers: the cp.async fast path with the PTX op loop, 3 CTAs of 128 threads per SM
+static tile_kernel_t select_kernel(int threads, int ctas, bool full, bool bulk, bool ptx, bool db, bool sc = false) {
+    // passes with single-control ops: the flavour of the PTX op loop that has those arms (3 CTAs per SM only)
+    if (sc && !full && ptx) {
+        if (threads == 256)
+            return bulk ? k_tile_pass<256, 2, false, true, true, false, true> : k_tile_pass<256, 2, false, false, true, false, true>;
+        if (db) return bulk ? k_tile_pass<128, 3, false, true, true, true, true> : k_tile_pass<128, 3, false, false, true, true, true>;
+        return bulk ? k_tile_pass<128, 3, false, true, true, false, true> : k_tile_pass<128, 3, false, false, true, false, true>;
+    }
+    // two tile buffers: the fast path with the PTX op loop, 3 CTAs of 128 threads per SM
     if (db && threads == 128 && !full && ptx)
         return bulk ? k_tile_pass<128, 3, false, true, true, true> : k_tile_pass<128, 3, false, false, true, true>;
     if (threads == 256) return pick_kernel<256, 2>(full, bulk, ptx);
@@ -1200,11 +1212,13 @@ int tile_kernel_setup() {
     for (int full = 0; full < 2; ++full)
         for (int bulk = 0; bulk < 2; ++bulk)
             for (int ptx = 0; ptx < 2; ++ptx)
-                for (int cfg = 0; cfg < 5; ++cfg) {
-                    const tile_kernel_t k = select_kernel(cfg == 0 ? 256 : 128, cfg == 1 ? 3 : cfg == 4 ? 5 : 4, full, bulk, ptx, cfg == 3);
-                    ok = ok && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    (int)TILE_SMEM_MAX) == cudaSuccess;
-                }
+                for (int cfg = 0; cfg < 5; ++cfg)
+                    for (int sc = 0; sc < 2; ++sc) {
+                        const tile_kernel_t k = select_kernel(cfg == 0 ? 256 : 128, cfg == 1 ? 3 : cfg == 4 ? 5 : 4, full, bulk,
+                                                              ptx, cfg == 3, sc != 0);
+                        ok = ok && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                        (int)TILE_SMEM_MAX) == cudaSuccess;
+                    }
     done[dev] = ok;
     return ok ? 0 : -1;
 }
@@ -1231,7 +1245,7 @@ int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, con
     bool db = want_db && threads == 128 && hdr.T == 11 && !hdr.full && knobs.ptx_ops &&
               2 * (tile_smem_bytes(hdr, threads, true) + 1024) <= TILE_SMEM_MAX;
     const tile_kernel_t kern = select_kernel(threads == 256 ? 256 : 128, knobs.ctas_per_sm, hdr.full != 0, bulk,
-                                             knobs.ptx_ops != 0, db);
+                                             knobs.ptx_ops != 0, db, hdr.uses_sc != 0);
     const size_t smem = tile_smem_bytes(hdr, threads, db);
     if (smem > TILE_SMEM_MAX) return -1;
     int per_sm = 0;
