@@ -184,7 +184,8 @@ int qvnt_reg_sync(qvnt_reg_t *reg);
  * leaves it local -- logical -> physical qubit map; 0: exchange and write back);
  * "peer_chunk_bits", "peer_tile_bits" (the same two sizes for passes that start on a global
  * qubit); "single_ctrl" (1, default: diagonal ops with one control in a register slot run
- * through their own arms; 0: the generic predicated ones); "double_buffer" (0; 1: two tile buffers
+ * through their own arms; 0: the generic predicated ones); "butterfly" (1, default: an uncontrolled
+ * h adds / subtracts and its 1/sqrt(2) is folded into another gate of the pass); "double_buffer" (0; 1: two tile buffers
  * per CTA, 2: only for passes that read a peer shard), "prefetch" (experiments, off); "profile" (0/1: time every launch with CUDA
  * events); "seed". */
 int qvnt_reg_set_option(qvnt_reg_t *reg, const char *key, int64_t value);

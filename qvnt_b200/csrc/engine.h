@@ -88,8 +88,11 @@ enum MCode : uint8_t {
 //          DU: no target bit in a register slot; DS: exactly one (slot j); DG: any a_reg
 //   FC_SW  x whose target AND a control sit in register slots: the selected pairs trade places
 //   FC_LX / FC_LI  "lazy" x: a permutation that costs no data movement, see below
-// The codes are DENSE (0 .. FC_COUNT-1, + FC_MASKED variants) so the interpreter's switch is one
-// jump table.
+// The codes are small and dense so the interpreter's switch is one jump table.  INVARIANT: every code
+// whose arm works on ONE register slot j has (code & 3) == j, in every variant (masked, control class,
+// single-control, butterfly): the op loop's prologue takes the slot's inversion byte -- hence the
+// coefficient block -- from the two low bits of the code byte.  So FC_MASKED and FC_TOTAL are
+// multiples of 4.
 enum FCode : uint8_t {
     FC_PR = 0,    // + slot
     FC_PX = 4,    // + slot
@@ -108,10 +111,10 @@ enum FCode : uint8_t {
                   //         bit in a register slot: their factors are multiplied into ONE complex number
                   //         per thread, applied to the 16 amplitudes once
     FC_COUNT = 17,
-    FC_MASKED = 17, // added to FC_PR / FC_PX / FC_DS / FC_DU / FC_DG / FC_DM codes when a control sits in a
+    FC_MASKED = 20, // added to FC_PR / FC_PX / FC_DS / FC_DU / FC_DG / FC_DM codes when a control sits in a
                     // register slot (okmask != 0xFFFF): per-slot-pattern predicates
-    FC_SW = 34,   // + slot (always masked)
-    FC_TOTAL = 38,
+    FC_SW = 40,   // + slot (always masked)
+    FC_TOTAL = 44,
     // The code byte of a fast MOp also carries the op's CONTROL CLASS: code = arm + FC_TOTAL * cls,
     // cls 0: unconditional, 1: controls on thread bits, 2: ... and outside the tile (MOP_COND /
     // MOP_CONDB say the same).  The PTX op loop jumps on the whole byte (class 1 lands in a stub that
@@ -122,16 +125,24 @@ enum FCode : uint8_t {
     // ONLY control sits in register slot c (qft's controlled phases).  The generic masked arms test a
     // predicate per slot pattern -- ptxas turns that into all the arithmetic plus a select per result,
     // 3x the instructions of the unmasked arm; these touch exactly the 8 patterns with bit c set.
-    FC_DS1 = 114, // + 4 * j + c: FC_MASKED + FC_DS + j with okmask == "slot bit c set"
-    FC_DU1 = 130, // + c: FC_MASKED + FC_DU
-    FC_DM1 = 134, // + c: FC_MASKED + FC_DM
-    FC_SPECIAL_END = 138
+    FC_DS1 = 132, // + 4 * c + j: FC_MASKED + FC_DS + j with okmask == "slot bit c set"  (code & 3 == j: the prologue
+                  //   of the op loop takes the target slot's inversion byte from the two low bits of the code)
+    FC_DU1 = 148, // + c: FC_MASKED + FC_DU
+    FC_DM1 = 152, // + c: FC_MASKED + FC_DM
+    // BUTTERFLY h (class 0, no control anywhere): FC_PR + j with coefficients (1, 1, 1, -1) -- the arm adds and
+    // subtracts (32 FP64 instructions instead of 64) and ignores the coefficient block.  The gate's 1/sqrt(2) is a
+    // factor on EVERY amplitude, so the planner multiplies the factors of a pass's butterflies into the
+    // coefficients of one unconditional pair op of the same pass (planner.cu, flush).
+    FC_HB = 156,  // + j
+    FC_SPECIAL_END = 160
 };
 // the generic (masked) code a single-control byte stands for; any other byte unchanged
 __host__ __device__ inline uint32_t fc_generic(uint32_t byte) {
     if (byte < (uint32_t)FC_DS1 || byte >= (uint32_t)FC_SPECIAL_END) return byte;
-    if (byte < (uint32_t)FC_DU1) return (uint32_t)(FC_MASKED + FC_DS) + ((byte - (uint32_t)FC_DS1) >> 2);
-    return byte < (uint32_t)FC_DM1 ? (uint32_t)(FC_MASKED + FC_DU) : (uint32_t)(FC_MASKED + FC_DM);
+    if (byte < (uint32_t)FC_DU1) return (uint32_t)(FC_MASKED + FC_DS) + ((byte - (uint32_t)FC_DS1) & 3u);
+    if (byte < (uint32_t)FC_DM1) return (uint32_t)(FC_MASKED + FC_DU);
+    if (byte < (uint32_t)FC_HB) return (uint32_t)(FC_MASKED + FC_DM);
+    return (uint32_t)FC_PR + (byte - (uint32_t)FC_HB);
 }
 constexpr uint8_t MOP_SKIP0 = 0x02;   // flags bit 1 (diagonal forms): f0 == 1, even parity untouched
 constexpr uint8_t MOP_COND = 0x04;    // flags bit 2: the op has controls on thread bits or outside the tile
@@ -223,6 +234,7 @@ struct TileKnobs {
     int prefetch = 0;      // 1: cp.async.bulk.prefetch.L2 of tile i+1 while tile i computes (measured: no gain, off)
     int double_buffer = 0; // 1: two tile buffers per CTA (2^11 tiles); 2: only for passes that read a peer shard
     int single_ctrl = 1;   // planner: single-control arms (FC_DS1 / FC_DU1 / FC_DM1) instead of the generic masked ones
+    int butterfly = 1;     // planner: uncontrolled h as add / subtract (FC_HB), its scale folded into another op of the pass
     int ptx_ops = 1;       // 1: the fast interpreter's op loop as one inline-PTX block (fastops_ptx.inc); 0: C++ loop
 };
 int launch_tile_pass(cudaStream_t st, const Segs &segs, const TPassHdr &hdr, const TStage *d_stages,

@@ -7,7 +7,7 @@ Why PTX: the C++ switch compiles to a compare tree plus divergence bookkeeping (
 by hand, an unconditional op costs: the (prefetched) header, two coefficient loads, the jump-table
 load and the indirect branch -- ~17 instructions -- and the FP64 body.  Everything an op only
 SOMETIMES needs is kept off that path:
-  * controls on thread bits: the op's code carries a class (code = arm + 38 * cls), class 1 jumps to a
+  * controls on thread bits: the op's code carries a class (code = arm + 44 * cls), class 1 jumps to a
     stub that tests the controls and re-dispatches (or skips the op);
   * controls outside the tile (class 2) are the same for the whole tile: before a tile's first stage
     the kernel rewrites those code bytes into the class 0 / 1 code or a skip code (tile.cu, patch_codes),
@@ -30,8 +30,9 @@ w3 = a_reg | idx << 16, c0..c3 at +16, alt block at +48.  Codes: engine.h FCode.
 import sys
 
 NV = 16
-FC_PR, FC_PX, FC_DS, FC_DU, FC_DG, FC_LX, FC_LI, FC_DM, FC_MASKED, FC_SW, FC_TOTAL = 0, 4, 8, 12, 13, 14, 15, 16, 17, 34, 38
-FC_DS1, FC_DU1, FC_DM1 = 114, 130, 134      # one control in register slot c, no other control (engine.h)
+FC_PR, FC_PX, FC_DS, FC_DU, FC_DG, FC_LX, FC_LI, FC_DM, FC_MASKED, FC_SW, FC_TOTAL = 0, 4, 8, 12, 13, 14, 15, 16, 20, 40, 44
+FC_DS1, FC_DU1, FC_DM1 = 132, 148, 152      # one control in register slot c, no other control (engine.h)
+FC_HB = 156                                 # butterfly h on slot j (engine.h)
 SKIP0, COND, PARB, CONDB, ATHR, STATIC = 0x02 << 8, 0x04 << 8, 0x08 << 8, 0x10 << 8, 0x20 << 8, 0x40 << 8
 MOP = 80
 
@@ -133,7 +134,7 @@ def gen(sc):
     flavours (tile.cu, template parameter SC) and a pass without such ops runs the lean one: the arms are
     never executed there, but one asm block is ONE register-allocation problem for ptxas, and with them
     in it the arms of a random circuit came out 3 % slower (A/B on one box, profiles/r02s_ab.txt)."""
-    arm = ["$TOP"] * FC_TOTAL            # the arms proper
+    arm = ["$BAD"] * FC_TOTAL            # the arms proper (a code nobody emits traps)
     for j in range(4):
         arm[FC_PR + j] = f"$PR{j}"
         arm[FC_PX + j] = f"$PX{j}"
@@ -149,16 +150,18 @@ def gen(sc):
     arm[FC_LI] = "$LI"
     arm[FC_DM] = "$DM"
     arm[FC_MASKED + FC_DM] = "$MDM"
-    # first-level table: masked arms go through $MPRE; classes 1 / 2 (code + 38, + 76) through the stubs
-    t1 = [("$MPRE" if (FC_MASKED <= c and arm[c] != "$TOP") else arm[c]) for c in range(FC_TOTAL)]
+    # first-level table: masked arms go through $MPRE; class 1 (code + 44) through its stub
+    t1 = [("$MPRE" if (FC_MASKED <= c and arm[c] != "$BAD") else arm[c]) for c in range(FC_TOTAL)]
     # class 2 (controls outside the tile) never reaches the loop: the kernel rewrites those code bytes
     # for every tile (tile.cu, patch_codes) into the class 0 / 1 code or one of the two skip codes
-    tbl = t1 + ["$C1"] * FC_TOTAL + ["$TOP"] * FC_TOTAL
-    tbl += ["$TOP"] * (256 - len(tbl))
+    tbl = t1 + ["$C1"] * FC_TOTAL + ["$BAD"] * FC_TOTAL
+    tbl += ["$BAD"] * (256 - len(tbl))
+    for j in range(4):
+        tbl[FC_HB + j] = f"$HB{j}"
     for c in range(4):
         for j in range(4):
             if j != c:
-                tbl[FC_DS1 + 4 * j + c] = f"$DS{j}c{c}" if sc else "$BAD"
+                tbl[FC_DS1 + 4 * c + j] = f"$DS{j}c{c}" if sc else "$BAD"      # (code & 3 == j: the prologue's blk)
         tbl[FC_DU1 + c] = f"$DUc{c}" if sc else "$BAD"
         tbl[FC_DM1 + c] = f"$DMc{c}" if sc else "$BAD"
     tbl[253] = "$SKIPRUN"                # engine.h MOP_NOP_RUN: a switched-off run header takes its members with it
@@ -266,6 +269,26 @@ def gen(sc):
             g = pred(K, True)
             swap(K, K | b, g)
         e("bra.uni $TOP;")
+
+    # ---- butterfly h on slot j: (p0 + p1, p0 - p1); with the slot inverted (blk != 0) register K holds p1 ----
+    sect("hot")
+    for j in range(4):
+        b = 1 << j
+        e(f"$HB{j}:")
+        e("setp.ne.u32 pk, blk, 0;")
+        e(f"@pk bra $HB{j}i;")
+        for inv in (False, True):
+            if inv:
+                e(f"$HB{j}i:")
+            for K in range(NV):
+                if K & b:
+                    continue
+                lo_, hi_ = (K | b, K) if inv else (K, K | b)        # lo_ holds p0, hi_ holds p1
+                for comp in (X, Y):
+                    e(f"sub.rn.f64 ta, {comp(lo_)}, {comp(hi_)};")
+                    e(f"add.rn.f64 {comp(lo_)}, {comp(lo_)}, {comp(hi_)};")
+                    e(f"mov.f64 {comp(hi_)}, ta;")
+            e("bra.uni $TOP;")
 
     # ---- diagonal, one target bit in register slot j ----
     def ds_arm(lab, j, masked, only=None):
@@ -586,9 +609,8 @@ def gen(sc):
         e("bra.uni $TOP;")
 
     sect("cold")
-    if not sc:
-        e("$BAD:")                  # a single-control code in the lean flavour: a launch-selection bug, fail loudly
-        e("trap;")
+    e("$BAD:")                      # a code without an arm (a single-control code in the lean flavour, an unpatched
+    e("trap;")                      # class-2 code): a planner / launch-selection bug -- fail loudly
     e("$END:")
     e("}")
     out = SECT["hot"] + SECT["warm"] + SECT["cold"]

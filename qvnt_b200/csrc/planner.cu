@@ -49,6 +49,7 @@ struct PlanCfg {
                               // gates per NVLink exchange
     int force_pinned = -1;    // restore_layout: the local bit a remap pass must trade the global bit with
     bool single_ctrl = true;  // single-control arms for diagonal forms with one control in a register slot
+    bool butterfly = true;    // uncontrolled h as a butterfly (FC_HB), its scale folded into another op of the pass
     uint64_t q_mask() const { return q_num >= 64 ? ~0ull : ((1ull << q_num) - 1ull); }
 };
 
@@ -623,6 +624,8 @@ static int build_plan(const PlanCfg &c, std::vector<POp> &pl, Plan &plan) {
         cur.hdr.stage_begin = (uint32_t)plan.stages.size();
         cur.hdr.op_begin = (uint32_t)plan.mops.size();
         int cur_static = 0;
+        double pass_scale = 1.0;      // product of the factors of the pass's butterfly h (FC_HB), folded at flush
+        const bool use_butterfly = c.butterfly;
         auto flush = [&]() {
             cur.hdr.n_static = (uint32_t)cur_static;
             cur_static = 0;
@@ -632,11 +635,33 @@ static int build_plan(const PlanCfg &c, std::vector<POp> &pl, Plan &plan) {
                 cur.hdr.stage_end[k] = (uint16_t)(plan.stages[cur.hdr.stage_begin + k].op_end - cur.hdr.op_begin);
             cur.hdr.need_flags = 0;
             cur.hdr.uses_sc = 0;
+            if (pass_scale != 1.0 && !cur.hdr.full) {
+                // the butterflies' common factor: into the first unconditional, unmasked pair op of the pass (it runs
+                // on every amplitude of every tile); a pass without one turns its last butterfly back into a pair op
+                MOp *carrier = nullptr, *last_hb = nullptr;
+                for (uint32_t k = 0; k < cur.hdr.n_ops; ++k) {
+                    MOp &mk = plan.mops[cur.hdr.op_begin + k];
+                    if (mk.code >= (uint8_t)FC_HB && mk.code < (uint8_t)(FC_HB + TILE_R)) last_hb = &mk;
+                    else if (!carrier && mk.code < (uint8_t)(FC_PX + TILE_R) && mk.okmask == 0xFFFFu &&
+                             !(mk.dagger & (MOP_COND | MOP_CONDB)))
+                        carrier = &mk;
+                }
+                if (!carrier && last_hb) {
+                    last_hb->code = (uint8_t)(FC_PR + (last_hb->code - FC_HB));
+                    carrier = last_hb;
+                }
+                if (carrier) {
+                    carrier->ph_re *= pass_scale; carrier->ph_im *= pass_scale;
+                    carrier->c2 *= pass_scale; carrier->c3 *= pass_scale;
+                    for (int q = 0; q < 4; ++q) carrier->alt[q] *= pass_scale;
+                }
+            }
+            pass_scale = 1.0;
             uint32_t member_until = 0;
             for (uint32_t k = 0; k < cur.hdr.n_ops; ++k) {
                 MOp &mk = plan.mops[cur.hdr.op_begin + k];
                 mk.idx = (uint16_t)k;
-                if (!cur.hdr.full && mk.code < (uint8_t)FC_TOTAL) {
+                if (!cur.hdr.full && mk.code < (uint8_t)FC_TOTAL) {      // (butterflies already carry their final code)
                     const int cls = (mk.dagger & MOP_CONDB) ? 2 : (mk.dagger & MOP_COND) ? 1 : 0;
                     // one control, in register slot c: the single-control arm (engine.h FC_DS1 ...); the members
                     // of a run are data of their header, their codes stay
@@ -650,14 +675,14 @@ static int build_plan(const PlanCfg &c, std::vector<POp> &pl, Plan &plan) {
                     const uint8_t g = mk.code;
                     if (cls == 0 && c1 >= 0 && k >= member_until && c.single_ctrl) {
                         if (g >= (uint8_t)(FC_MASKED + FC_DS) && g < (uint8_t)(FC_MASKED + FC_DS + TILE_R))
-                            mk.code = (uint8_t)(FC_DS1 + 4 * (g - (FC_MASKED + FC_DS)) + c1);
+                            mk.code = (uint8_t)(FC_DS1 + 4 * c1 + (g - (FC_MASKED + FC_DS)));
                         else if (g == (uint8_t)(FC_MASKED + FC_DU)) mk.code = (uint8_t)(FC_DU1 + c1);
                         else if (g == (uint8_t)(FC_MASKED + FC_DM)) mk.code = (uint8_t)(FC_DM1 + c1);
                     }
                     if (g == (uint8_t)FC_DM || g == (uint8_t)(FC_MASKED + FC_DM)) member_until = k + 1u + mk.a_reg;
                     if (mk.code < (uint8_t)FC_TOTAL)                  // control class into the code byte (engine.h)
                         mk.code = (uint8_t)(mk.code + FC_TOTAL * cls);
-                    else cur.hdr.uses_sc = 1;
+                    else if (mk.code < (uint8_t)FC_HB) cur.hdr.uses_sc = 1;
                 }
                 const MBase &mb = plan.bases[cur.hdr.op_begin + k];
                 if (mb.ctrl_base | mb.a_base) cur.hdr.need_flags = 1;
@@ -775,7 +800,17 @@ static int build_plan(const PlanCfg &c, std::vector<POp> &pl, Plan &plan) {
                     };
                     switch (p.d.kind) {
                     // h1.rs:16-22: (p0 + p1) * s, (p0 - p1) * s
-                    case QVNT_H1: pair4(FC_PR, c, c, c, -c); break;
+                    case QVNT_H1:
+                        if (use_butterfly && !creg && !cthr && !b.ctrl_base) {
+                            // add / subtract only; the factor (1/sqrt(2), or the 1 / 0.5 of a split h2) goes into
+                            // the pass's scale and from there into one pair op's coefficients (flush)
+                            pair4(FC_PR, 1.0, 1.0, 1.0, -1.0);
+                            m.code = (uint8_t)(FC_HB + ss.ra);
+                            pass_scale *= p.d.ph_re;
+                        } else {
+                            pair4(FC_PR, p.d.ph_re, p.d.ph_re, p.d.ph_re, -p.d.ph_re);
+                        }
+                        break;
                     case QVNT_RY: pair4(FC_PR, c, -sn, sn, c); break;
                     case QVNT_RX: pair4(FC_PX, c, sn, sn, c); break;
                     case QVNT_Y: pair4(FC_PX, 0.0, 1.0, -1.0, 0.0); break;
@@ -1074,6 +1109,7 @@ static PlanCfg cfg_of(const qvnt_reg *r) {
     c.peer_chunk_bits = r->opt_peer_chunk_bits;
     c.peer_tile_bits = r->opt_peer_tile_bits;
     c.single_ctrl = r->knobs.single_ctrl != 0;
+    c.butterfly = r->knobs.butterfly != 0;
     c.ack_cap = r->ack_cap;
     memcpy(c.perm, r->perm, sizeof(c.perm));
     return c;

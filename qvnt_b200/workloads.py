@@ -180,3 +180,27 @@ def qasm_config5(n: int, layers: int, seed: int = 0x51415335) -> str:
             out.append(f"rx(pi/{2 + layer % 5}) q[{pick(1)[0]}];")
     out.append("measure q -> c;")
     return "\n".join(out) + "\n"
+
+
+def fast_mix(n: int, layers: int, seed: int) -> MultiOp:
+    """Every kind the fast stage interpreter carries, with random controls (incl. multi-bit masks): x / cx
+    leave register slots inverted, controlled diagonals and h follow on the same slots."""
+    rng = SplitMix64(seed)
+    circ = MultiOp()
+    for _ in range(layers):
+        k = rng.next() % 11
+        b = 1 << (rng.next() % n)
+        m = (rng.next() & ((1 << n) - 1)) or 1
+        th = rng.angle()
+        g = [op.x(m), op.y(m), op.z(m), op.s(m), op.t(m), op.h(m), op.rx(th, b), op.ry(th, b), op.rz(th, b),
+             op.rzz(th, b | (1 << ((b.bit_length() + 2) % n)) if b != 1 << ((b.bit_length() + 2) % n) else b | (b << 1) % (1 << n) or 3),
+             op.t(m).dgr()][k]
+        if rng.next() % 3 == 0:
+            free = ((1 << n) - 1) & ~g.act_on()
+            for s_ in g:
+                free &= ~(s_.a_mask | s_.b_mask)
+            c = free & rng.next() & rng.next()
+            if c:
+                g = g.c(c)
+        circ *= g
+    return circ

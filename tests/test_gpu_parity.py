@@ -148,6 +148,21 @@ def test_mixed_circuit_all_kinds(oracle, n, fuse):
     assert abs(g.get_absolute() - o.get_absolute()) <= PROB_TOL
 
 
+@pytest.mark.parametrize("n,layers,seed", [(12, 500, 3), (16, 400, 11), (20, 250, 5)])
+@pytest.mark.parametrize("opts", [{}, {"single_ctrl": 0, "butterfly": 0}, {"ptx_ops": 0}])
+def test_fast_interpreter_forms_with_inverted_slots(oracle, n, layers, seed, opts):
+    """x / cx leave register slots inverted (lazy); controlled phases, rz, h and rotations follow on the
+    same slots: the single-control arms, the butterfly h, the generic masked arms and the C++ loop must
+    all pick the exchanged coefficient block / predicates."""
+    circ = workloads.fast_mix(n, layers, seed)
+    g, o = both(oracle, n, seed=seed)
+    for k, v in opts.items():
+        g.set_option(k, v)
+    g.apply(circ)
+    o.apply(circ)
+    assert_close(g, o)
+
+
 @pytest.mark.parametrize("n,depth", [(12, 20), (18, 10), (22, 4)])
 def test_random_layered_config2_scaled(oracle, n, depth):
     # configs[1] generator at oracle-feasible sizes

@@ -59,27 +59,7 @@ def _state(n, seed):
     return v / np.linalg.norm(v)
 
 
-def _fast_mix(n, layers, seed):
-    """Every kind the fast interpreter carries, with random controls (incl. multi-bit masks)."""
-    rng = workloads.SplitMix64(seed)
-    circ = MultiOp()
-    for _ in range(layers):
-        k = rng.next() % 11
-        b = 1 << (rng.next() % n)
-        m = (rng.next() & ((1 << n) - 1)) or 1
-        th = rng.angle()
-        g = [op.x(m), op.y(m), op.z(m), op.s(m), op.t(m), op.h(m), op.rx(th, b), op.ry(th, b), op.rz(th, b),
-             op.rzz(th, b | (1 << ((b.bit_length() + 2) % n)) if b != 1 << ((b.bit_length() + 2) % n) else b | (b << 1) % (1 << n) or 3),
-             op.t(m).dgr()][k]
-        if rng.next() % 3 == 0:
-            free = ((1 << n) - 1) & ~g.act_on()
-            for s_ in g:
-                free &= ~(s_.a_mask | s_.b_mask)
-            c = free & rng.next() & rng.next()
-            if c:
-                g = g.c(c)
-        circ *= g
-    return circ
+_fast_mix = workloads.fast_mix
 
 
 @pytest.mark.parametrize("n,circ_fn", [

@@ -15,23 +15,29 @@ from __future__ import annotations
 
 import numpy as np
 
-FC_PR, FC_PX, FC_DS, FC_DU, FC_DG, FC_LX, FC_LI, FC_DM, FC_MASKED, FC_SW = 0, 4, 8, 12, 13, 14, 15, 16, 17, 34
-FC_TOTAL = 38
+FC_PR, FC_PX, FC_DS, FC_DU, FC_DG, FC_LX, FC_LI, FC_DM, FC_MASKED, FC_SW = 0, 4, 8, 12, 13, 14, 15, 16, 20, 40
+FC_TOTAL = 44
 MOP_SKIP0, MOP_COND, MOP_PARB, MOP_CONDB, MOP_ATHR, MOP_STATIC = 0x02, 0x04, 0x08, 0x10, 0x20, 0x40
 NV = 16
-FC_DS1, FC_DU1, FC_DM1, FC_SPECIAL_END = 114, 130, 134, 138
+FC_DS1, FC_DU1, FC_DM1, FC_HB, FC_SPECIAL_END = 132, 148, 152, 156, 160
 
 
 def generic_code(m) -> int:
     """The single-control arms (engine.h FC_DS1 / FC_DU1 / FC_DM1: one control in register slot c, no
-    other control) compute what the generic masked arm computes under okmask = 'slot bit c set'."""
+    other control) compute what the generic masked arm computes under okmask = 'slot bit c set'; the
+    butterfly h (FC_HB + j) is FC_PR + j with the coefficients (1, 1, 1, -1) its descriptor carries."""
     c = m.code
     if not (FC_DS1 <= c < FC_SPECIAL_END):
         return c
     assert not (m.flags & (MOP_COND | MOP_CONDB)) and m.ctrl_thr == 0 and m.ctrl_base == 0
+    if c >= FC_HB:
+        assert m.okmask == 0xFFFF and tuple(m.c) == (1.0, 1.0, 1.0, -1.0) and tuple(m.alt) == (-1.0, 1.0, 1.0, 1.0)
+        assert (c & 3) == c - FC_HB, "the op loop takes the slot's inversion byte from code & 3"
+        return FC_PR + (c - FC_HB)
     if c < FC_DU1:
-        j, ctl = (c - FC_DS1) >> 2, (c - FC_DS1) & 3
+        ctl, j = (c - FC_DS1) >> 2, (c - FC_DS1) & 3
         assert j != ctl
+        assert (c & 3) == j, "the op loop takes the target slot's inversion byte from code & 3"
         g = FC_MASKED + FC_DS + j
     elif c < FC_DM1:
         ctl = c - FC_DU1
@@ -41,6 +47,8 @@ def generic_code(m) -> int:
         g = FC_MASKED + FC_DM
     assert m.okmask == sum(1 << K for K in range(NV) if K & (1 << ctl)), "single-control arm with another okmask"
     return g
+
+
 U64 = (1 << 64) - 1
 
 
@@ -158,6 +166,7 @@ def run_stage(tile: np.ndarray, st, T: int, gbase: int):
         okm = okmask(m, masked)
         if code < FC_DS:                                       # pair forms on slot s
             s = code & 3
+            assert (m.code & 3) == s, "engine.h invariant: the op loop takes the slot's inversion byte from code & 3"
             form = code - s
             bit = 1 << s
             inv = (ib >> s) & 1
@@ -197,6 +206,7 @@ def run_stage(tile: np.ndarray, st, T: int, gbase: int):
                 regs[sel, K] *= f[sel]
         elif FC_DS <= code < FC_DU:
             s = code - FC_DS
+            assert (m.code & 3) == s, "engine.h invariant: the op loop takes the slot's inversion byte from code & 3"
             bit = 1 << s
             par = dpar(m)
             blk = ((ib >> s) & 1) ^ par                         # 1: the alt block (roles exchanged)

@@ -13,9 +13,10 @@ sys.path.insert(0, ROOT)
 from qvnt_b200 import plan, workloads  # noqa: E402
 
 NAMES = {0: "pair_real", 4: "pair_cross", 8: "diag_slot", 12: "diag_thread", 13: "diag_generic", 14: "lazy_x_thread",
-         15: "lazy_x_slot", 16: "diag_run_header", 34: "swap_x(ctrl in slot)"}
+         15: "lazy_x_slot", 16: "diag_run_header", 40: "swap_x(ctrl in slot)"}
 COST = {"pair_real": 80, "pair_cross": 80, "diag_thread": 78, "diag_slot": 80,
         "diag_generic": 120, "swap_x(ctrl in slot)": 70,      # (48 moves where the control holds)
+        "butterfly_h": 56, "single-control diag_slot": 50, "single-control diag_thread": 55, "single-control diag_run_header": 60,
         "lazy_x_thread": 16, "lazy_x_slot": 10, "diag_run_header": 80, "diag_run_member": 14}
 
 
@@ -48,13 +49,16 @@ def main():
                     skip -= 1
                     continue
                 raw = m.code
-                if 114 <= raw < 138:          # single-control arms (engine.h FC_DS1 / FC_DU1 / FC_DM1)
-                    cnt["single-control " + ("diag_slot" if raw < 130 else "diag_thread" if raw < 134 else "diag_run_header")] += 1
-                    if raw >= 134:
+                if 132 <= raw < 156:          # single-control arms (engine.h FC_DS1 / FC_DU1 / FC_DM1)
+                    cnt["single-control " + ("diag_slot" if raw < 148 else "diag_thread" if raw < 152 else "diag_run_header")] += 1
+                    if raw >= 152:
                         skip = m.a_reg
                     continue
-                c = raw % 38
-                c = c - 17 if 17 <= c < 34 else c
+                if 156 <= raw < 160:          # butterfly h (FC_HB)
+                    cnt["butterfly_h"] += 1
+                    continue
+                c = raw % 44
+                c = c - 20 if 20 <= c < 40 else c
                 base = max(k for k in NAMES if k <= c)
                 cnt[NAMES[base]] += 1
                 if base == 16:
