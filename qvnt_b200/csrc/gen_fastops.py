@@ -271,10 +271,13 @@ def gen(sc):
         e("bra.uni $TOP;")
 
     # ---- butterfly h on slot j: (p0 + p1, p0 - p1); with the slot inverted (blk != 0) register K holds p1 ----
+    # Two FP64 instructions per component and no move: sum = p0 + p1 in place, then the difference as
+    # sum - 2 * p1 in p1's register (one extra rounding of the sum, ~1e-16 relative).
     sect("hot")
     for j in range(4):
         b = 1 << j
         e(f"$HB{j}:")
+        e("mov.f64 ta, 0dC000000000000000;")          # -2.0
         e("setp.ne.u32 pk, blk, 0;")
         e(f"@pk bra $HB{j}i;")
         for inv in (False, True):
@@ -285,9 +288,8 @@ def gen(sc):
                     continue
                 lo_, hi_ = (K | b, K) if inv else (K, K | b)        # lo_ holds p0, hi_ holds p1
                 for comp in (X, Y):
-                    e(f"sub.rn.f64 ta, {comp(lo_)}, {comp(hi_)};")
                     e(f"add.rn.f64 {comp(lo_)}, {comp(lo_)}, {comp(hi_)};")
-                    e(f"mov.f64 {comp(hi_)}, ta;")
+                    e(f"fma.rn.f64 {comp(hi_)}, {comp(hi_)}, ta, {comp(lo_)};")
             e("bra.uni $TOP;")
 
     # ---- diagonal, one target bit in register slot j ----

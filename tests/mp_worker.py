@@ -28,6 +28,8 @@ def build_circuit(name, n):
         return op.qft((1 << n) - 1) * workloads.mixed_all_kinds(n, 40, seed=11)
     if name == "layered":
         return workloads.random_layered(n, 8)
+    if name == "fast_mix":       # controlled forms on register slots that lazy x left inverted
+        return workloads.fast_mix(n, 300, seed=9) * workloads.random_layered(n, 3)
     raise SystemExit(f"unknown circuit {name}")
 
 

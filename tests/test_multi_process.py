@@ -48,7 +48,7 @@ def _worlds():
 def test_multi_process_parity(world):
     if world not in _worlds():
         pytest.skip("8 ranks only on an 8-GPU box")
-    res = run_workers(world, 22, ["layered+mixed", "qft+mixed"])
+    res = run_workers(world, 22, ["layered+mixed", "qft+mixed", "fast_mix"])
     for r in res["results"]:
         assert r["max_abs_err"] <= 1e-10, r
         assert r["max_abs_err_after_collapse"] <= 1e-10, r
