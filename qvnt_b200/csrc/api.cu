@@ -1150,6 +1150,7 @@ int qvnt_reg_set_option(qvnt_reg_t *r, const char *key, int64_t value) {
     else if (!strcmp(key, "ptx_ops")) r->knobs.ptx_ops = value != 0;
     else if (!strcmp(key, "single_ctrl")) r->knobs.single_ctrl = value != 0;
     else if (!strcmp(key, "butterfly")) r->knobs.butterfly = value != 0;
+    else if (!strcmp(key, "lower_two_bit")) r->knobs.lower_two_bit = value != 0;
     else if (!strcmp(key, "double_buffer")) r->knobs.double_buffer = value < 0 || value > 2 ? 0 : (int)value;
     else if (!strcmp(key, "tile_ctas")) {
         if (value != 0 && (value < 3 || value > 5)) {

@@ -50,6 +50,7 @@ struct PlanCfg {
     int force_pinned = -1;    // restore_layout: the local bit a remap pass must trade the global bit with
     bool single_ctrl = true;  // single-control arms for diagonal forms with one control in a register slot
     bool butterfly = true;    // uncontrolled h as a butterfly (FC_HB), its scale folded into another op of the pass
+    bool lower_two_bit = true; // swap / i_swap / rxx / ryy in op lists as products of kinds the fast interpreter has
     uint64_t q_mask() const { return q_num >= 64 ? ~0ull : ((1ull << q_num) - 1ull); }
 };
 
@@ -161,6 +162,58 @@ static int lower_ops(const PlanCfg &r, const qvnt_op_t *ops, size_t n_ops, std::
                 q.mix = q.d.a;
                 q.dg = q.d.ctrl;
                 pl.push_back(q);
+            }
+            continue;
+        }
+        if (split_fused && r.lower_two_bit && pc64(o.a_mask) == 2 &&
+            (o.kind == QVNT_SWAP || o.kind == QVNT_ISWAP || o.kind == QVNT_RXX || o.kind == QVNT_RYY)) {
+            // Two-bit kinds the fast stage interpreter has no form for, as products of kinds it has (a pass
+            // with one full-interpreter op runs the full interpreter for ALL its ops):
+            //   swap(a, b)    = cx(a->b) cx(b->a) cx(a->b)                      (swap.rs:16-22; exact)
+            //   i_swap(a, b)  = swap(a, b) * diag(1, i, i, 1),  diag = s(a) s(b) cz(a, b)   (i_swap.rs:20-37; exact)
+            //   rxx(a, b)     = h(a) h(b) rzz(a, b) h(a) h(b)                   (X(x)X = (H(x)H)(Z(x)Z)(H(x)H))
+            //   ryy(a, b)     = s(a) s(b) rxx(a, b) s^-1(a) s^-1(b)             (Y = S X S^-1)
+            // Controls go on the middle factor only where the outer ones cancel without it.
+            const uint64_t ba = o.a_mask & (~o.a_mask + 1), bb = o.a_mask & ~ba;
+            auto emit = [&](uint32_t kind, uint64_t a, uint64_t ctrl, uint32_t dagger, double re, double im) {
+                POp q;
+                memset(&q, 0, sizeof(q));
+                q.src = (uint32_t)k;
+                q.cls = op_class(kind);
+                q.d.kind = kind;
+                q.d.dagger = dagger;
+                q.d.a = a;
+                q.d.ctrl = ctrl;
+                q.d.ph_re = re;
+                q.d.ph_im = im;
+                q.mix = q.cls == CLS_PAIR ? a : 0;
+                q.dg = ctrl | (q.cls == CLS_DIAG ? a : 0);
+                pl.push_back(q);
+            };
+            const uint32_t dg = o.dagger ? 1u : 0u;
+            if (o.kind == QVNT_SWAP || o.kind == QVNT_ISWAP) {
+                if (o.kind == QVNT_ISWAP) {
+                    emit(QVNT_S, ba, o.ctrl, dg, 0.0, 0.0);
+                    emit(QVNT_S, bb, o.ctrl, dg, 0.0, 0.0);
+                    emit(QVNT_Z, bb, o.ctrl | ba, 0u, 0.0, 0.0);
+                }
+                emit(QVNT_X, bb, o.ctrl | ba, 0u, 0.0, 0.0);
+                emit(QVNT_X, ba, o.ctrl | bb, 0u, 0.0, 0.0);
+                emit(QVNT_X, bb, o.ctrl | ba, 0u, 0.0, 0.0);
+            } else {
+                if (o.kind == QVNT_RYY) {
+                    emit(QVNT_S, ba, 0, 1u, 0.0, 0.0);
+                    emit(QVNT_S, bb, 0, 1u, 0.0, 0.0);
+                }
+                emit(QVNT_H1, ba, 0, 0u, QV_FRAC_1_SQRT_2, 0.0);
+                emit(QVNT_H1, bb, 0, 0u, QV_FRAC_1_SQRT_2, 0.0);
+                emit(QVNT_RZZ, o.a_mask, o.ctrl, dg, o.phase_re, o.phase_im);
+                emit(QVNT_H1, ba, 0, 0u, QV_FRAC_1_SQRT_2, 0.0);
+                emit(QVNT_H1, bb, 0, 0u, QV_FRAC_1_SQRT_2, 0.0);
+                if (o.kind == QVNT_RYY) {
+                    emit(QVNT_S, ba, 0, 0u, 0.0, 0.0);
+                    emit(QVNT_S, bb, 0, 0u, 0.0, 0.0);
+                }
             }
             continue;
         }
@@ -1110,6 +1163,7 @@ static PlanCfg cfg_of(const qvnt_reg *r) {
     c.peer_tile_bits = r->opt_peer_tile_bits;
     c.single_ctrl = r->knobs.single_ctrl != 0;
     c.butterfly = r->knobs.butterfly != 0;
+    c.lower_two_bit = r->knobs.lower_two_bit != 0;
     c.ack_cap = r->ack_cap;
     memcpy(c.perm, r->perm, sizeof(c.perm));
     return c;

@@ -65,6 +65,7 @@ def check_structure(passes, q_num, world=1, rank=0):
 
 
 SPLIT_KINDS = {op.K_X, op.K_Y, op.K_Z, op.K_S, op.K_T}     # multi-bit masks are scheduled bit by bit
+LOWERED_KINDS = {op.K_SWAP, op.K_ISWAP, op.K_RXX, op.K_RYY}  # two-bit kinds scheduled as products of fast kinds
 
 
 def planned_sequence(passes, circ):
@@ -75,6 +76,17 @@ def planned_sequence(passes, circ):
     for p in passes:
         for o in p.all_ops():
             s = src[o.src].clone()
+            if s.kind in LOWERED_KINDS and o.kind != s.kind:
+                # swap / i_swap / rxx / ryy of an op list are scheduled as products of fast kinds
+                # (planner.cu lower_ops): rebuild the factor from what the planner reports
+                assert o.a & ~s.a_mask == 0 and o.ctrl & ~(s.ctrl | s.a_mask) == 0
+                if o.kind == op.K_RZZ:
+                    f = SingleOp(op.K_RZZ, o.a, phase=s.phase)
+                else:
+                    f = SingleOp(o.kind, o.a, dagger=bool(o.dagger))
+                    assert o.kind in (op.K_X, op.K_Z, op.K_S, op.K_H1)
+                out.append(f.c(o.ctrl) if o.ctrl else f)
+                continue
             assert s.ctrl == o.ctrl
             if s.kind == op.K_H2 and o.kind == op.K_H1:
                 assert o.a in (s.a_mask, s.b_mask)
@@ -98,6 +110,9 @@ def every_op_scheduled_once(passes, circ):
     for p in passes:
         for o in p.all_ops():
             seen.setdefault(o.src, 0)
+            if circ[o.src].kind in LOWERED_KINDS and o.kind != circ[o.src].kind:
+                seen[o.src] = -1                       # (the product's factors: checked by the replay)
+                continue
             if o.kind in SPLIT_KINDS or (o.kind == op.K_H1 and circ[o.src].kind == op.K_H2):
                 assert seen[o.src] & o.a == 0
                 seen[o.src] |= o.a
