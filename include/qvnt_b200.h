@@ -131,7 +131,9 @@ int qvnt_reg_apply(qvnt_reg_t *reg, const qvnt_op_t *ops, size_t n_ops);
 
 /* The schedule qvnt_reg_apply would run for this op list on rank `rank` of a q_num-qubit
  * register sharded over `world` GPUs, as text (one line per pass / stage / op).  Host-only:
- * needs no CUDA device.  tile_bits / chunk_bits 0 = defaults.  *needed = bytes incl. NUL. */
+ * needs no CUDA device.  tile_bits / chunk_bits 0 = defaults.  *needed = bytes incl. NUL.
+ * peers_attached: 0 / 1, 3 = attached with option "remap" off; fuse: 0 / 1, 3 = with option
+ * "lower_two_bit" on. */
 int qvnt_plan_describe(uint32_t q_num, uint32_t rank, uint32_t world, int peers_attached, int fuse,
                        int tile_bits, int chunk_bits, const qvnt_op_t *ops, size_t n_ops, char *out,
                        size_t cap, size_t *needed);
@@ -185,7 +187,9 @@ int qvnt_reg_sync(qvnt_reg_t *reg);
  * "peer_chunk_bits", "peer_tile_bits" (the same two sizes for passes that start on a global
  * qubit); "single_ctrl" (1, default: diagonal ops with one control in a register slot run
  * through their own arms; 0: the generic predicated ones); "butterfly" (1, default: an uncontrolled
- * h adds / subtracts and its 1/sqrt(2) is folded into another gate of the pass); "double_buffer" (0; 1: two tile buffers
+ * h adds / subtracts and its 1/sqrt(2) is folded into another gate of the pass); "lower_two_bit"
+ * (0, default; 1: swap / i_swap / rxx / ryy of an op list run as products of cx, s, z, h, rzz so
+ * that their pass needs no full interpreter -- measured slower on configs[4]); "double_buffer" (0; 1: two tile buffers
  * per CTA, 2: only for passes that read a peer shard), "prefetch" (experiments, off); "profile" (0/1: time every launch with CUDA
  * events); "seed". */
 int qvnt_reg_set_option(qvnt_reg_t *reg, const char *key, int64_t value);

@@ -234,7 +234,8 @@ struct TileKnobs {
     int prefetch = 0;      // 1: cp.async.bulk.prefetch.L2 of tile i+1 while tile i computes (measured: no gain, off)
     int double_buffer = 0; // 1: two tile buffers per CTA (2^11 tiles); 2: only for passes that read a peer shard
     int single_ctrl = 1;   // planner: single-control arms (FC_DS1 / FC_DU1 / FC_DM1) instead of the generic masked ones
-    int lower_two_bit = 1; // planner: swap / i_swap / rxx / ryy of an op list as products of fast kinds (no full-interpreter pass)
+    int lower_two_bit = 0; // planner: swap / i_swap / rxx / ryy of an op list as products of fast kinds (no full-interpreter
+                           //   pass); off: measured slower on configs[4] (planner.cu lower_ops)
     int butterfly = 1;     // planner: uncontrolled h as add / subtract (FC_HB), its scale folded into another op of the pass
     int ptx_ops = 1;       // 1: the fast interpreter's op loop as one inline-PTX block (fastops_ptx.inc); 0: C++ loop
 };

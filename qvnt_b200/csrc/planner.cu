@@ -50,7 +50,8 @@ struct PlanCfg {
     int force_pinned = -1;    // restore_layout: the local bit a remap pass must trade the global bit with
     bool single_ctrl = true;  // single-control arms for diagonal forms with one control in a register slot
     bool butterfly = true;    // uncontrolled h as a butterfly (FC_HB), its scale folded into another op of the pass
-    bool lower_two_bit = true; // swap / i_swap / rxx / ryy in op lists as products of kinds the fast interpreter has
+    bool lower_two_bit = false; // swap / i_swap / rxx / ryy in op lists as products of kinds the fast interpreter has
+                                // (option; off: measured slower on the 36-qubit QASM circuit, see lower_ops)
     uint64_t q_mask() const { return q_num >= 64 ? ~0ull : ((1ull << q_num) - 1ull); }
 };
 
@@ -174,6 +175,10 @@ static int lower_ops(const PlanCfg &r, const qvnt_op_t *ops, size_t n_ops, std::
             //   rxx(a, b)     = h(a) h(b) rzz(a, b) h(a) h(b)                   (X(x)X = (H(x)H)(Z(x)Z)(H(x)H))
             //   ryy(a, b)     = s(a) s(b) rxx(a, b) s^-1(a) s^-1(b)             (Y = S X S^-1)
             // Controls go on the middle factor only where the outer ones cancel without it.
+            // OFF by default (option "lower_two_bit"): configs[4] at 36 qubits on 8 GPUs ran 1.98 s with it
+            // against 1.66 s without (profiles/r02w_, r02u_sharded_36q_qasm_8gpu.json) -- three controlled
+            // swaps of register slots cost more than the full interpreter's one permutation, and a cx whose
+            // target is a global qubit asks for a remap pass of its own.
             const uint64_t ba = o.a_mask & (~o.a_mask + 1), bb = o.a_mask & ~ba;
             auto emit = [&](uint32_t kind, uint64_t a, uint64_t ctrl, uint32_t dagger, double re, double im) {
                 POp q;
@@ -1379,7 +1384,8 @@ int describe_plan(uint32_t q_num, uint32_t rank, uint32_t world, int peers, int 
     c.peer_chunk_bits = tile_bits ? 0 : 6;     // the library defaults (reg.h) unless the caller fixes the geometry
     c.peer_tile_bits = tile_bits ? 0 : 12;
     for (uint32_t q = 0; q < 64; ++q) c.perm[q] = (uint8_t)q;
-    c.fuse = fuse != 0;
+    c.fuse = (fuse & 1) != 0;
+    c.lower_two_bit = (fuse & 2) != 0;       // (fuse == 3: with option "lower_two_bit")
     c.tile_bits = tile_bits;
     c.chunk_bits = chunk_bits;
     std::vector<POp> pl;

@@ -81,13 +81,15 @@ def _ints(s: str) -> List[int]:
 
 
 def describe(q_num: int, circ, rank: int = 0, world: int = 1, peers: bool = False, fuse: bool = True,
-             tile_bits: int = 0, chunk_bits: int = 0, remap: bool = True) -> List[PlanPass]:
+             tile_bits: int = 0, chunk_bits: int = 0, remap: bool = True,
+             lower_two_bit: bool = False) -> List[PlanPass]:
     if isinstance(circ, SingleOp):
         circ = MultiOp([circ])
     arr, n = circ.to_c_array()
     need = c_size_t(0)
     lib = _ffi.lib()
-    args = (q_num, rank, world, (1 if remap else 3) if peers else 0, int(fuse), tile_bits, chunk_bits, arr, n)
+    args = (q_num, rank, world, (1 if remap else 3) if peers else 0, (3 if lower_two_bit else 1) if fuse else 0,
+            tile_bits, chunk_bits, arr, n)
     _ffi.check(lib.qvnt_plan_describe(*args, None, 0, byref(need)))
     buf = ctypes.create_string_buffer(need.value)
     _ffi.check(lib.qvnt_plan_describe(*args, buf, need.value, byref(need)))

@@ -137,11 +137,12 @@ def test_every_kind_single_sweep(oracle, n, fuse):
 
 
 @pytest.mark.parametrize("n", [6, 11, 16])
-@pytest.mark.parametrize("fuse", [0, 1])
+@pytest.mark.parametrize("fuse", [0, 1, 3])
 def test_mixed_circuit_all_kinds(oracle, n, fuse):
     circ = workloads.mixed_all_kinds(n, 150, seed=n)
     g, o = both(oracle, n, seed=n)
-    g.set_option("fuse", fuse)
+    g.set_option("fuse", fuse & 1)
+    g.set_option("lower_two_bit", fuse >> 1)      # 3: swap / i_swap / rxx / ryy as products of fast kinds
     g.apply(circ)
     o.apply(circ)
     assert_close(g, o, exact=(fuse == 0))

@@ -137,9 +137,14 @@ def every_op_scheduled_once(passes, circ):
     (12, lambda n: op.qft((1 << n) - 1) * op.h((1 << n) - 1)),
 ])
 @pytest.mark.parametrize("tile_bits,chunk_bits", [(0, 0), (8, 4), (6, 3)])
-def test_schedule_preserves_result(oracle, n, circ_fn, tile_bits, chunk_bits):
+@pytest.mark.parametrize("lower_two_bit", [False, True])
+def test_schedule_preserves_result(oracle, n, circ_fn, tile_bits, chunk_bits, lower_two_bit):
     circ = circ_fn(n)
-    passes = plan.describe(n, circ, tile_bits=tile_bits, chunk_bits=chunk_bits)
+    if lower_two_bit and not any(s.kind in LOWERED_KINDS for s in circ):
+        pytest.skip("no swap / i_swap / rxx / ryy in this circuit")
+    passes = plan.describe(n, circ, tile_bits=tile_bits, chunk_bits=chunk_bits, lower_two_bit=lower_two_bit)
+    if lower_two_bit:
+        assert any(o.kind != circ[o.src].kind and circ[o.src].kind in LOWERED_KINDS for p in passes for o in p.all_ops())
     check_structure(passes, n)
     every_op_scheduled_once(passes, circ)
     seq = planned_sequence(passes, circ)
