@@ -2,6 +2,7 @@
 interpreter (tests/tile_emulator.py), must reproduce the oracle's state: coefficient forms,
 slot / thread / tile splits of controls and diagonal masks, lazy x, merged diagonal runs, tile
 geometry -- and, for sharded registers, tile ownership and rank-dependent flags.  CPU only."""
+import os
 import numpy as np
 import pytest
 
@@ -103,3 +104,43 @@ def test_encoded_sharded_plan_reproduces_oracle(oracle, world):
     got, _, _, _ = _emulate(oracle, n, circ, v.copy(), world=world, remap=False)
     assert _emulate.last_remaps == 0
     assert np.abs(got - want).max() <= 1e-12
+
+
+# ---------------------------------------------------------------- the op loop's code numbering
+def _engine_codes():
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    txt = open(os.path.join(root, "qvnt_b200", "csrc", "engine.h")).read()
+    return {k: int(v) for k, v in re.findall(r"\b(FC_[A-Z0-9_]+|MOP_END|MOP_NOP|MOP_NOP_RUN)\s*=\s*(\d+)", txt)}
+
+
+def test_code_numbering_is_consistent():
+    """engine.h is the definition; the PTX generator and the emulator restate it.  Every code whose arm
+    works on one register slot must keep code & 3 == slot in every variant (the loop's prologue reads
+    the slot's inversion byte from the code's low bits): the bases are multiples of 4."""
+    import importlib.util
+    c = _engine_codes()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_fastops", os.path.join(root, "qvnt_b200", "csrc", "gen_fastops.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    for name in ("FC_PR", "FC_PX", "FC_DS", "FC_DU", "FC_DG", "FC_LX", "FC_LI", "FC_DM", "FC_MASKED", "FC_SW", "FC_TOTAL",
+                 "FC_DS1", "FC_DU1", "FC_DM1", "FC_HB"):
+        assert getattr(gen, name) == c[name], name
+        if hasattr(emu, name):
+            assert getattr(emu, name) == c[name], name
+    assert emu.FC_SPECIAL_END == c["FC_SPECIAL_END"]
+    for base in ("FC_PR", "FC_PX", "FC_DS", "FC_MASKED", "FC_SW", "FC_TOTAL", "FC_DS1", "FC_HB"):
+        assert c[base] % 4 == 0, base
+    assert 3 * c["FC_TOTAL"] <= c["FC_DS1"] and c["FC_SPECIAL_END"] <= c["MOP_NOP_RUN"] < c["MOP_NOP"] < c["MOP_END"] == 255
+
+
+def test_generated_ptx_is_current(tmp_path):
+    """fastops_ptx.inc is committed (the build does not need python); it must be what the generator emits."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "qvnt_b200", "csrc")
+    out = tmp_path / "fastops_ptx.inc"
+    subprocess.run([sys.executable, os.path.join(src, "gen_fastops.py"), str(out)], check=True, capture_output=True)
+    assert out.read_text() == open(os.path.join(src, "fastops_ptx.inc")).read()
