@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """Generates fastops_ptx.inc: the op loop of the FAST stage interpreter (tile.cu) as ONE inline-PTX
-block -- header fetch, a single `brx.idx` jump table and every arm.
+block -- header fetch, a single `brx.idx` jump table and every arm -- in two flavours: QV_FASTOPS_PTX
+(lean) and QV_FASTOPS_PTX_SC (plus the single-control arms; see gen()).
 
 Why PTX: the C++ switch compiles to a compare tree plus divergence bookkeeping (BSSY / BSYNC / BREAK),
 ~40 instructions and several dependent branches per op around 64 FP64 instructions of work.  Written
@@ -16,6 +17,9 @@ SOMETIMES needs is kept off that path:
     predicate mask (and permutes it by the inverted slots);
   * diagonal ops with target bits outside the register slots, merged runs, lazy x: the arm re-reads the
     header words it needs.
+INVARIANT the prologue relies on: a code whose arm works on ONE register slot j has code & 3 == j in every
+variant (masked, class 1, single-control, butterfly) -- `blk`, the inversion byte of that slot, picks the
+coefficient block.  tests/test_tile_emulator.py checks the numbering against engine.h.
 
 Operands of the asm statement (tile.cu, stage_ops_fast_ptx):
   %0..%31  the 16 register-resident amplitudes, v[K].x = %(2K), v[K].y = %(2K+1)      ("+d")
