@@ -144,3 +144,27 @@ def test_generated_ptx_is_current(tmp_path):
     out = tmp_path / "fastops_ptx.inc"
     subprocess.run([sys.executable, os.path.join(src, "gen_fastops.py"), str(out)], check=True, capture_output=True)
     assert out.read_text() == open(os.path.join(src, "fastops_ptx.inc")).read()
+
+
+# ---------------------------------------------------------------- butterfly h: the scale travels
+def _count_codes(n, circ, lo, hi, **kw):
+    return sum(1 for p in plan.describe(n, circ, **kw) if not p.direct for st in p.stages for m in st.mops if lo <= m.code < hi)
+
+
+@pytest.mark.parametrize("n,circ_fn", [
+    # passes made of butterflies only: the last one turns back into a pair op that carries the product
+    (13, lambda n: op.h((1 << n) - 1)),
+    # single h1 gates (scale 1/sqrt2 each) around lazy inversions of their slots and a carrier of the crossed form
+    (12, lambda n: MultiOp([op.single.h1(1 << q) for q in range(n)]) * op.x(0b101).c(0b10) *
+         MultiOp([op.single.h1(1 << q) for q in range(n)]) * op.rx(0.3, 1 << 5) * op.x(1 << 7) * op.h(0b11 << 6)),
+    # controlled h is NOT a butterfly (its factor is not on every amplitude); it may be the carrier only if unconditional
+    (12, lambda n: op.h(0b1111).c(1 << 9) * op.h((1 << n) - 1) * op.rz(0.7, 1 << 3).c(1 << 4) * op.h(0b110000)),
+])
+@pytest.mark.parametrize("tile_bits,chunk_bits", [(0, 0), (8, 3)])
+def test_butterfly_h_scale_is_folded(oracle, n, circ_fn, tile_bits, chunk_bits):
+    circ = circ_fn(n)
+    assert _count_codes(n, circ, emu.FC_HB, emu.FC_HB + 4, tile_bits=tile_bits, chunk_bits=chunk_bits) >= 4
+    v = _state(n, 3)
+    got, n_fast, _, _ = _emulate(oracle, n, circ, v.copy(), tile_bits=tile_bits, chunk_bits=chunk_bits)
+    assert n_fast >= 1
+    assert np.abs(got - _oracle_apply(oracle, n, v, circ)).max() <= 1e-12
