@@ -1,5 +1,6 @@
 #!/bin/bash
 # A/B on ONE box: the previous commit's library (build_tmp/wt, A) against the current one (B), interleaved
+# A = the previous commit built in a worktree:  git worktree add build_tmp/wt <commit> && make -C build_tmp/wt/qvnt_b200/csrc
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -x --timeout 400 > gpurun_out/r02s_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02s_pytest.log; tail -3 gpurun_out/r02s_pytest.log
 timeout 300 python tools/bisect_mix.py > gpurun_out/r02s_bisect.txt 2>&1; cat gpurun_out/r02s_bisect.txt
