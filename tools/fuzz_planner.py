@@ -39,44 +39,50 @@ def circuit(rng, n):
     return c
 
 
+def one_case(seed):
+    """-> ("ok" | "skip" | "fail", description)"""
+    rng = np.random.default_rng(seed)
+    world = int(rng.choice([1, 1, 2, 4, 8]))
+    n = int(rng.integers(max(7, 6 + world.bit_length() - 1), 14))
+    n_local = n - (world.bit_length() - 1)
+    kw = {}
+    if rng.integers(0, 2):
+        T = int(rng.integers(6, min(12, n_local) + 1))
+        kw["tile_bits"] = T
+        kw["chunk_bits"] = int(rng.integers(2, T + 1))
+    if world > 1 and rng.integers(0, 3) == 0:
+        kw["remap"] = False
+    if rng.integers(0, 2):
+        kw["lower_two_bit"] = True
+    circ = circuit(rng, n)
+    v = _state(n, seed)
+    what = f"seed={seed} n={n} world={world} kw={kw} ops={len(circ)}"
+    try:
+        got = _emulate(oracle, n, circ, v.copy(), world=world, **kw)[0]
+        err = float(np.abs(got - _oracle_apply(oracle, n, v, circ)).max())
+        return ("ok" if err <= 1e-12 else "fail"), f"{what} err={err}"
+    except AssertionError as ex:
+        if "full-interpreter remap passes" in str(ex):      # the emulator has no full interpreter: GPU tests cover these
+            return "skip", what
+        return "fail", f"{what} {ex!r}"[:300]
+    except Exception as ex:          # planner error
+        return "fail", f"{what} {ex!r}"[:300]
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 300.0
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     t0 = time.time()
     done = skipped = 0
     while time.time() - t0 < budget:
-        rng = np.random.default_rng(seed)
-        world = int(rng.choice([1, 1, 2, 4, 8]))
-        n = int(rng.integers(max(7, 6 + world.bit_length() - 1), 14))
-        n_local = n - (world.bit_length() - 1)
-        kw = {}
-        if rng.integers(0, 2):
-            T = int(rng.integers(6, min(12, n_local) + 1))
-            kw["tile_bits"] = T
-            kw["chunk_bits"] = int(rng.integers(2, T + 1))
-        if world > 1 and rng.integers(0, 3) == 0:
-            kw["remap"] = False
-        if rng.integers(0, 2):
-            kw["lower_two_bit"] = True
-        circ = circuit(rng, n)
-        v = _state(n, seed)
-        try:
-            got = _emulate(oracle, n, circ, v.copy(), world=world, **kw)[0]
-            err = float(np.abs(got - _oracle_apply(oracle, n, v, circ)).max())
-            bad = err > 1e-12
-        except AssertionError as ex:
-            if "full-interpreter remap passes" in str(ex):      # the emulator has no full interpreter: GPU tests cover these
-                skipped += 1
-                seed += 1
-                continue
-            err, bad = repr(ex)[:200], True
-        except Exception as ex:          # planner error
-            err, bad = repr(ex)[:200], True
-        if bad:
-            print(f"FAIL seed={seed} n={n} world={world} kw={kw} ops={len(circ)} err={err}", flush=True)
-        done += 1
+        st, what = one_case(seed)
+        if st == "fail":
+            print("FAIL", what, flush=True)
+        done += st != "skip"
+        skipped += st == "skip"
         seed += 1
-    print(f"{done} cases checked, {skipped} skipped (full-interpreter remap pass) in {time.time() - t0:.0f} s, last seed {seed - 1}", flush=True)
+    print(f"{done} cases checked, {skipped} skipped (full-interpreter remap pass) in {time.time() - t0:.0f} s, last seed {seed - 1}",
+          flush=True)
 
 
 if __name__ == "__main__":
